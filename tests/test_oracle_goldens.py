@@ -1,0 +1,258 @@
+"""Pin the CPU oracle to the reference's own golden outputs.
+
+tests/golden/testref_kat.json holds the numbers extracted from /root/reference/testref/*.ref and the
+option strings of /root/reference/Makefile:254-513 (tests/golden/make_golden.py).  No GPU needed.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def _sig(x, ref_text):
+    """relative tolerance implied by the digits printed in the golden (%g -> 6 significant)."""
+    return 6e-6 * abs(float(ref_text))
+
+
+def _nums(lines):
+    import re
+    return np.array([float(t) for l in lines for t in re.findall(r"[+-]\d\.\d+e[+-]\d+", l)])
+
+
+def _problem(kat, name, extra=""):
+    c = kat[name]
+    opts = c["options"].replace("-options_file abf.opts", " ".join(kat["_abf_opts"]))
+    return O.Problem(opts + " " + extra, nsd=c["nsd"], lame=c["lame"]), c
+
+
+# ---- C.1: ||F||_2 = iteration-0 residual of every unpreconditioned-norm (right PC) golden ----------------
+RIGHT_PC_CASES = ["exSaddle3d_ar_1", "exSaddle3d_pseudoice_1", "exSaddle2d_ar_1", "exSaddle3d_mg_1", "exSaddle2d_mg_1",
+                  "exSaddle3d_lame_mg_1", "exSaddle2d_lame_mg_1", "exSaddle3d_lame_3", "exSaddle3d_lame_4",
+                  "exSaddle3d_lame_5", "exSaddle3d_ildl_1"]
+
+
+@pytest.mark.parametrize("name", RIGHT_PC_CASES)
+def test_rhs_norm_matches_golden(kat, name):
+    c = kat[name]
+    # only the discretisation options matter for ||F||; solver options are ignored here
+    o = O.parse_options(c["options"].replace("-options_file abf.opts", ""))
+    p = O.Problem({k: v for k, v in o.items() if not k.startswith("saddle_") and k not in ("mg", "fs", "nlevels")},
+                  nsd=c["nsd"], lame=c["lame"])
+    f = np.linalg.norm(p.F())
+    assert abs(f - c["residuals"][0]) <= _sig(f, c["residuals_text"][0]), (f, c["residuals_text"][0])
+
+
+# ---- C.2: pattern / size pins from -ksp_view goldens ----------------------------------------------------
+@pytest.mark.parametrize("m,rows,nnz,alloc", [(2, 402, 52546, 100794), (4, 2312, 381196, 542628), (6, 6934, 1244446, 1585590)])
+def test_pattern_counts_3d(m, rows, nnz, alloc):
+    p = O.Problem("-mx %d -model 0" % m, nsd=3)
+    assert (p.n, p.nnz, p.prealloc) == (rows, nnz, alloc)
+    A = p.A()
+    # closed forms of SURVEY App. A.5
+    assert p.submatrix(0, 0).ia[-1] == 9 * (8 * m + 1) ** 3
+    assert p.submatrix(0, 1).ia[-1] == 3 * (5 * m + 1) ** 3
+    assert p.submatrix(1, 1).ia[-1] == (3 * m + 1) ** 3
+    assert p.mnnz == (3 * m + 1) ** 3
+    # columns strictly ascending in every row
+    for i in range(0, p.n, 7):
+        r = A.ja[A.ia[i]:A.ia[i + 1]]
+        assert np.all(np.diff(r) > 0)
+
+
+def test_pattern_counts_2d():
+    m = 5
+    p = O.Problem("-mx %d -model 0" % m, nsd=2)
+    assert p.submatrix(0, 0).ia[-1] == 4 * (8 * m + 1) ** 2
+    assert p.submatrix(0, 1).ia[-1] == 2 * (5 * m + 1) ** 2
+    assert p.submatrix(1, 1).ia[-1] == (3 * m + 1) ** 2
+
+
+def test_noncubic_pattern_is_product_of_directions():
+    p = O.Problem("-mx 4 -my 7 -mz 5 -model 1", nsd=3)
+    assert p.submatrix(0, 0).ia[-1] == 9 * (8 * 4 + 1) * (8 * 7 + 1) * (8 * 5 + 1)
+
+
+def test_galerkin_level_sizes_match_ksp_view(kat):
+    p, c = _problem(kat, "exSaddle3d_pseudoice_1")
+    r = p.pc_setup()
+    assert list(r.level_rows[:3]) == [192, 1029, 6591]
+    assert list(r.level_nnz[:3]) == [9000, 61731, 1058841]
+    assert [6591, 6591, 1] in c["mat_rows"] and [1058841, 1058841] in c["mat_nnz"]
+    assert [89373, 89373] in c["mat_nnz"] and p.submatrix(0, 1).ia[-1] == 89373
+    assert [1244446, 1585590] in c["mat_nnz"]
+
+
+# ---- C.3: diagnostics blocks of the Jacobi-GMRES goldens (fixed iteration count => digits must match) ----
+@pytest.mark.parametrize("name", ["exSaddle2d_1", "exSaddle3d_1"])
+def test_jacobi_gmres_diagnostics_exact(kat, name):
+    p, c = _problem(kat, name)
+    x, r = p.solve()
+    assert r.its == c["iterations"] and r.reason == -3 and c["reason"] == "DIVERGED_ITS"
+    got = p.diagnostics_text(x)
+    assert [g.rstrip() for g in got] == [s.rstrip() for s in c["diagnostics"]]
+    assert p.banner.rstrip("\n").split("\n") == c["banner"]
+
+
+@pytest.mark.parametrize("name", ["exSaddle3d_lame_1", "exSaddle2d_lame_1"])
+def test_lame_jacobi_gmres_converges_like_golden(kat, name):
+    p, c = _problem(kat, name)
+    x, r = p.solve()
+    # summation order moves long Jacobi-GMRES runs by one iteration (testref/exSaddle2d_lame_1 vs _2: 145 vs 146)
+    assert abs(r.its - c["iterations"]) <= 1 and r.reason == 2
+    got = _nums(p.diagnostics_text(x)); ref = _nums(c["diagnostics"])
+    assert np.allclose(got, ref, rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["exSaddle3d_lame_3", "exSaddle3d_lame_4", "exSaddle3d_lame_5"])
+def test_right_jacobi_gmres_history(kat, name):
+    p, c = _problem(kat, name)
+    x, r = p.solve()
+    assert r.nhist == len(c["residuals"])
+    for i, t in enumerate(c["residuals_text"]):
+        assert abs(r.hist[i] - float(t)) <= _sig(r.hist[i], t), (i, r.hist[i], t)
+    assert [g.rstrip() for g in p.diagnostics_text(x)] == [s.rstrip() for s in c["diagnostics"]]
+
+
+# ---- C.3/C.4: the ABF solver (north-star tree) --------------------------------------------------------
+def test_abf_pseudoice_history_with_golden_chebyshev_bounds(kat):
+    """exSaddle3d_pseudoice_1: all 21 residuals to the printed digits once the golden's own Chebyshev
+    bounds (testref/exSaddle3d_pseudoice_1.ref:103,132) replace the irreproducible noisy estimate (App. B.4)."""
+    c = kat["exSaddle3d_pseudoice_1"]
+    (e1lo, e1hi), (e2lo, e2hi) = c["cheb_bounds"][0], c["cheb_bounds"][1]
+    p, c = _problem(kat, "exSaddle3d_pseudoice_1",
+                    "-saddle_fieldsplit_u_mg_levels_1_ksp_chebyshev_eigenvalues %r,%r "
+                    "-saddle_fieldsplit_u_mg_levels_2_ksp_chebyshev_eigenvalues %r,%r" % (e1lo, e1hi, e2lo, e2hi))
+    x, r = p.solve()
+    assert r.its == 20 and r.reason == 2 and r.nhist == 21
+    for i, t in enumerate(c["residuals_text"]):
+        # bounds are given to 6 digits, so allow 2 units in the 6th digit
+        assert abs(r.hist[i] - float(t)) <= 2 * _sig(r.hist[i], t), (i, r.hist[i], t)
+
+
+def test_abf_ar_3d_iteration_counts(kat):
+    p, c = _problem(kat, "exSaddle3d_ar_1")
+    x, r = p.solve()
+    assert r.its == len(c["residuals"]) - 1 == 6
+    assert list(r.inner_its[:r.n_inner]) == c["inner_its"] == [7, 5, 5, 7, 6, 6]
+    # own noise vector: histories agree to 1e-3..3e-2 relative (App. C.4)
+    for i, t in enumerate(c["residuals"]):
+        assert abs(r.hist[i] - t) <= 3e-2 * t
+
+
+def test_abf_ar_2d_iteration_count_within_one(kat):
+    p, c = _problem(kat, "exSaddle2d_ar_1")
+    x, r = p.solve()
+    assert abs(r.its - (len(c["residuals"]) - 1)) <= 1
+    for i in range(5):
+        assert abs(r.hist[i] - c["residuals"][i]) <= 1e-2 * c["residuals"][i]
+
+
+def test_chebyshev_ritz_estimates_close_to_golden(kat):
+    """The Ritz extremes depend on PETSc's unknown noise vector; ours land within 1% for emax."""
+    p, c = _problem(kat, "exSaddle3d_pseudoice_1")
+    r = p.pc_setup()
+    assert abs(r.cheb_emax_est[1] - c["cheb_ritz"][0][1]) / c["cheb_ritz"][0][1] < 1e-2
+    assert abs(r.cheb_emax_est[2] - c["cheb_ritz"][1][1]) / c["cheb_ritz"][1][1] < 1e-2
+    assert abs(r.cheb_emax[1] - 1.1 * r.cheb_emax_est[1]) < 1e-14 and abs(r.cheb_emin[1] - 0.2 * r.cheb_emax_est[1]) < 1e-14
+
+
+# ---- direct-solve KATs: diagnostics of converged goldens at solver tolerance -----------------------------
+def test_direct_solve_matches_fs_golden(kat):
+    import scipy.sparse.linalg as spla
+    c = kat["exSaddle3d_fs_1"]
+    p = O.Problem("-model 2 -sinker_n 1 -mx 4", nsd=3)
+    x = spla.splu(p.A().scipy().tocsc()).solve(p.F())
+    got = _nums(p.diagnostics_text(x)); ref = _nums(c["diagnostics"])
+    assert np.allclose(got[-5:], ref[-5:], rtol=1e-5, atol=1e-6)  # pressure norms (golden stops at rtol 1e-5)
+    assert np.allclose(got[:-5], ref[:-5], rtol=5e-2, atol=1e-6)  # velocity ~1e-5 of the pressure scale
+
+
+def test_mms_error_norms(kat):
+    """exSaddle2d_mms_1: direct LU, model 101, constant-pressure null space (testref/exSaddle2d_mms_1.ref)."""
+    import scipy.sparse.linalg as spla
+    p = O.Problem("-model 101 -mx 16", nsd=2)
+    # pin one pressure dof through a bordered system to fix the null space, then project as MatNullSpaceRemove does
+    A = p.A().scipy().tolil(); F = p.F().copy()
+    k = p.nu
+    A[k, :] = 0; A[k, k] = 1.0; F[k] = 0.0
+    x = spla.splu(A.tocsc()).solve(F)
+    x[p.nu:] -= x[p.nu:].mean()      # MatNullSpaceRemove with the constant-pressure vector (exSaddle.c:288-301)
+    # left-preconditioned GMRES with an exact LU: the iteration-0 "residual" is ||A^-1 F|| = ||x||
+    assert abs(np.linalg.norm(x) - 255.134) < 2e-3
+    nx = 2 * 16 + 1
+    xs = np.arange(nx) / (nx - 1.0)
+    X, Y = np.meshgrid(xs, xs, indexing="xy")
+    uref = np.stack([20 * X * Y ** 3, 5 * (X ** 4 - Y ** 4)], axis=-1).reshape(-1)
+    eu = np.linalg.norm(uref - x[:p.nu])
+    assert abs(eu - 0.000198842) / 0.000198842 < 2e-2
+    assert abs(eu / np.linalg.norm(uref) - 1.20852e-06) / 1.20852e-06 < 2e-2
+
+
+# ---- unit checks of oracle helpers against numpy ---------------------------------------------------
+def test_hessenberg_eigenvalues_vs_numpy():
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 6, 10):
+        H = np.triu(rng.standard_normal((n, n)), -1)
+        e = np.sort_complex(O.hess_eig(H)); e0 = np.sort_complex(np.linalg.eigvals(H))
+        assert np.allclose(e, e0, rtol=1e-10, atol=1e-12)
+
+
+def test_rander48_stream_is_drand48():
+    v = O.rander48(4)
+    # first drand48() values after srand48(0x12345678): X1 = (a*X0+c) mod 2^48
+    X = ((0x12345678 << 16) | 0x330E)
+    ref = []
+    for _ in range(4):
+        X = (0x5DEECE66D * X + 0xB) & ((1 << 48) - 1); ref.append(X / float(1 << 48))
+    assert np.array_equal(v, np.array(ref))
+
+
+def test_ilu0_exact_on_tridiagonal_and_matches_dense_pattern_restricted():
+    import scipy.sparse as sp
+    p = O.Problem("-mx 3 -model 0", nsd=3)
+    M = p.Mp(); n = M.shape[0]
+    lu = np.empty_like(M.a)
+    assert O.lib().xo_ilu0(n, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
+    # reference ILU(0): dense IKJ restricted to the pattern
+    A = M.scipy().toarray(); pat = A != 0
+    for i in range(n):
+        for k in range(i):
+            if pat[i, k]:
+                A[i, k] = A[i, k] * (1.0 / A[k, k])
+                for j in range(k + 1, n):
+                    if pat[i, j] and pat[k, j]:
+                        A[i, j] -= A[i, k] * A[k, j]
+    LU = sp.csr_matrix((lu, M.ja, M.ia), shape=M.shape).toarray()
+    d = np.diag(LU).copy(); np.fill_diagonal(LU, 1.0 / d)
+    assert np.allclose(LU, A * pat, rtol=1e-12, atol=1e-14)
+    b = np.arange(n) * 0.1 - 1.0; x = np.empty(n)
+    O.lib().xo_ilu0_solve(n, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(b), O._dp(x))
+    L = np.tril(A * pat, -1) + np.eye(n); U = np.triu(A * pat)
+    assert np.allclose(x, np.linalg.solve(U, np.linalg.solve(L, b)), rtol=1e-11)
+
+
+def test_galerkin_and_transfers_vs_scipy(kat):
+    import scipy.sparse as sp
+    p = O.Problem("-mx 4 -my 2 -mz 2 -model 6 -eta1 100", nsd=3)
+    s = O.Solver(); O.lib().xo_solver_abf(s); s.mg_levels = 2
+    p.pc_setup(s)
+    A1 = p.mg_level(1).scipy(); A0 = p.mg_level(0).scipy()
+    nf = (9, 5, 5); nc = (5, 3, 3)
+
+    def P1(nf_, nc_):
+        P = np.zeros((nf_, nc_))
+        for f in range(nf_):
+            if f % 2 == 0:
+                P[f, f // 2] = 1.0
+            else:
+                P[f, f // 2] = 0.5; P[f, f // 2 + 1] = 0.5
+        return sp.csr_matrix(P)
+    Pn = sp.kron(P1(nf[2], nc[2]), sp.kron(P1(nf[1], nc[1]), P1(nf[0], nc[0])))
+    P = sp.kron(Pn, sp.identity(3)).tocsr()
+    G = (P.T @ A1 @ P).toarray()
+    assert np.allclose(A0.toarray(), G, rtol=1e-12, atol=1e-13)
+    assert A0.nnz == 9 * (3 * 5 - 2) * (3 * 3 - 2) * (3 * 3 - 2)
+    rng = np.random.default_rng(1)
+    xc = rng.standard_normal(P.shape[1]); xf = rng.standard_normal(P.shape[0])
+    assert np.allclose(p.prolong_add(0, xc, xf.copy()), xf + P @ xc, rtol=1e-13)
+    assert np.allclose(p.restrict(0, xf, P.shape[1]), P.T @ xf, rtol=1e-13)
