@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the exSaddle solve path on B200 (contract: see the task brief).
+
+Metric (BASELINE.json): Stokes KSP solve time to rtol 1e-8 (s) -- FGMRES + fieldsplit Schur-upper ABF with GMG
+(Chebyshev/Jacobi, Galerkin) on the velocity block -- and the Stokes MatMult HBM GB/s against the measured peak.
+A "step" is one KSPSolve of the assembled system (zero initial guess, second-solve protocol of exSaddle.c:569-599:
+set-up is outside the timed region).  Inputs (A00 alone is 10.4 GB at 64^3) are far larger than the 126 MB L2.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mx 64] [--eta1 1e6] [--levels 6] [--impl reference]
+
+N > 1 (torchrun): every rank solves its own independent replica of the workload (weak scaling, no collective on
+the data path; the slab-partitioned single-problem solve is not in this round) and value = mean solve time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ABF = ("-saddle_ksp_type fgmres -fs -saddle_fieldsplit_u_pc_type mg -saddle_fieldsplit_u_ksp_type gcr "
+       "-saddle_fieldsplit_u_ksp_rtol 1e-2 -saddle_fieldsplit_u_mg_levels_pc_type jacobi "
+       "-saddle_fieldsplit_u_mg_levels_ksp_type chebyshev -saddle_fieldsplit_u_mg_levels_ksp_chebyshev_esteig 0,0.2,0,1.1 "
+       "-saddle_fieldsplit_u_mg_levels_ksp_max_it 8 -saddle_fieldsplit_u_mg_levels_ksp_norm_type none "
+       "-saddle_fieldsplit_u_pc_mg_galerkin -saddle_fieldsplit_p_ksp_type preonly -saddle_fieldsplit_p_pc_type bjacobi")
+ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iterations.json")
+
+
+def workload_options(a):
+    return "%s -saddle_fieldsplit_u_pc_mg_levels %d -model 6 -mx %d -eta0 1 -eta1 %g -saddle_ksp_rtol 1e-8" % (ABF, a.levels, a.mx, a.eta1)
+
+
+def workload_name(a):
+    return "exSaddle3d Stokes sinker (model 6) %d^3 Q2-Q1, eta1/eta0=%g, FGMRES+fieldsplit Schur-upper ABF, GMG %d levels Chebyshev(8)/Jacobi Galerkin, rtol 1e-8" % (a.mx, a.eta1, a.levels)
+
+
+def config_key(a):
+    return "mx%d_eta%g_lv%d" % (a.mx, a.eta1, a.levels)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def a00_bytes(info, by_mode):
+    """Algorithmic bytes of one fine-level A00 BAIJ(3) launch, averaged over the launches of the solve:
+    (72+4) B per block + 4 B per block-row pointer + 8 B per vector entry streamed (x,y [+b,+idiag,+p_{k-1}])."""
+    rows, _, nnz, bs = info
+    nblk = nnz // (bs * bs)
+    mat = (8 * bs * bs + 4) * nblk + 4 * (rows // bs + 1)
+    vecs = {0: 2, 1: 3, 2: 4, 3: 5}
+    tot = sum(by_mode)
+    if tot == 0:
+        return mat + 16 * rows
+    return mat + 8 * rows * sum(vecs[m] * by_mode[m] for m in range(4)) / tot
+
+
+def cpu_reference(a, steps, warmup, emit):
+    """The reference's CPU implementation of the path.  PETSc is not installable here (no PETSc/MPI in the image),
+    so this is the oracle port (oracle/xo_*.c, OpenMP over all host cores), timed on a bounded sample:
+    `sample_outer` outer FGMRES iterations of the same system, scaled to the full solve's outer iteration count."""
+    from oracle import oracle as O
+    import ctypes as C
+    cores = O.lib().xo_num_threads()
+    opts = workload_options(a)
+    t0 = time.time()
+    p = O.Problem(opts, nsd=3)
+    s = p.solver()
+    r = p.pc_setup(s)
+    t_setup = time.time() - t0
+    its_full = None
+    if os.path.exists(ITERS_FILE):
+        its_full = json.load(open(ITERS_FILE)).get(config_key(a), {}).get("outer_its")
+    sample = a.sample_outer
+    s.max_outer_sample = sample
+    times = []
+    for i in range(warmup + steps):
+        x, res = p.solve(s)
+        if i >= warmup:
+            times.append(res.solve_seconds)
+    per_outer = (sum(times) / len(times)) / max(1, res.its)
+    if its_full is None or res.reason > 0:
+        its_full = res.its if res.reason > 0 else None
+    value = per_outer * its_full if its_full else None
+    base = {"value": value, "unit": "s", "cores": cores, "kind": "port",
+            "sample": "%d outer FGMRES iterations of the same %d^3 system on the oracle port (OpenMP, %d threads): %.3f s per outer iteration x %s outer iterations of the full solve; CPU set-up %.1f s not included"
+                      % (res.its, a.mx, cores, per_outer, its_full, t_setup)}
+    return base, per_outer, t_setup
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mx", type=int, default=64)
+    ap.add_argument("--eta1", type=float, default=1e6)
+    ap.add_argument("--levels", type=int, default=6)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sample-outer", dest="sample_outer", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    cfg = {"workload": workload_name(a), "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
+           "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one per GPU), no data-path collective" % world,
+           "l2": "inputs (A00 BAIJ 10.4 GB at 64^3) far exceed the 126 MB L2; no flush needed",
+           "options": workload_options(a)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        base, per_outer, t_setup = cpu_reference(a, max(1, a.steps), a.warmup, None)
+        line = {"impl": "reference", "metric": "stokes_ksp_solve_time_rtol1e-8", "value": base["value"], "unit": "s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": None if base["value"] is None else 1e3 * base["value"],
+                "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg, "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line)); return 0
+
+    import numpy as np
+    import torch
+    import exsaddle_b200 as X
+    if not torch.cuda.is_available() or not X.device_available():
+        raise SystemExit("bench.py needs a CUDA device: exsaddle_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    g = X.ExSaddle(workload_options(a) + " -xsb_time_kernels", nsd=3, device=local)
+    t0 = time.time(); g.assemble(); t_asm = time.time() - t0
+    t0 = time.time(); g.ksp_setup(); t_setup = time.time() - t0
+    n = g.n
+    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local))
+    xdev = torch.empty(n, dtype=torch.float64, device="cuda")
+    F_host = torch.from_numpy(g.rhs()).pin_memory()
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K solves, CUDA events on the launching stream
+    for _ in range(warmup):
+        g.solve_dev(0, xdev.data_ptr())
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0; a00_ns = []; a00_modes = [0, 0, 0, 0]; n_a00 = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(a.steps):
+            g.solve_dev(0, xdev.data_ptr())
+            c = g.counters(); launches += c["launches"]; a00_ns.append(c["a00_avg_ns"]); n_a00 += c["a00_spmv"]
+            a00_modes = [u + v for u, v in zip(a00_modes, c["a00_by_mode"])]
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    its, reason = g.iterations()
+    inner = g.inner_iterations()
+    hist = g.history()
+    # ---- end to end through the host-pointer C-ABI call: pinned host RHS -> device, solution -> host, every step
+    barrier()
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            g._chk(g.L.xsb_ksp_solve(g.h, X.api._dp(F_host.numpy()), X.api._dp(x_host.numpy())))
+        e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    sec_per_solve = ms / 1e3 / a.steps
+    e2e_per_solve = ms_e2e / 1e3 / a.steps
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        info = g.mat_info(X.MAT_A00)
+        bytes_launch = a00_bytes(info, a00_modes)
+        avg_ns = sum(a00_ns) / len(a00_ns)
+        achieved = bytes_launch / avg_ns if avg_ns else 0.0   # B/ns = GB/s
+        a_info = g.mat_info(X.MAT_A)
+        # full-A AIJ MatMult micro-measure (the reference's MATAIJ layout): 20 warm-up + 50 timed applies
+        xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
+        yout = torch.empty_like(xin)
+        with torch.cuda.stream(stream):
+            for _ in range(10):
+                g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(stream)
+            for _ in range(30):
+                g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
+            m1.record(stream)
+        torch.cuda.synchronize()
+        aij_ms = m0.elapsed_time(m1) / 30
+        aij_bytes = 12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]
+        roof = {"bound": "hbm", "kernel": "spmv_baij_kernel<3> (fine-level A00 with fused residual/Chebyshev epilogue)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
+                "launches_timed": n_a00, "share_of_step": (n_a00 * avg_ns * 1e-9) / (sec_per_solve * a.steps),
+                "aij_matmult": {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)", "ms": aij_ms, "bytes": aij_bytes,
+                                "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak}}
+        os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
+        try:
+            d = json.load(open(ITERS_FILE)) if os.path.exists(ITERS_FILE) else {}
+            d[config_key(a)] = {"outer_its": its, "inner_its_total": int(sum(inner)), "reason": reason}
+            json.dump(d, open(ITERS_FILE, "w"), indent=1, sort_keys=True)
+        except Exception:
+            pass
+        base = None
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                import psutil
+                need_gb = 45.0 * (a.mx / 64.0) ** 3
+                if psutil.virtual_memory().available / 2 ** 30 > need_gb + 8:
+                    base, _, _ = cpu_reference(a, 1, 0, None)
+                else:
+                    base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped: host RAM below %.0f GB" % need_gb}
+            except Exception as e:   # the checker must never take the bench line down
+                base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+        line = {"metric": "stokes_ksp_solve_time_rtol1e-8", "value": sec_per_solve, "unit": "s", "n_gpus": world, "steps": a.steps,
+                "warmup": warmup, "ms_per_step": 1e3 * sec_per_solve, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg,
+                "solve": {"outer_its": its, "reason": reason, "inner_gcr_its": int(sum(inner)), "rnorm0": float(hist[0]), "rnorm": float(hist[-1]),
+                          "a00_spmv_per_solve": n_a00 // a.steps, "assemble_s": t_asm, "ksp_setup_s": t_setup},
+                "roofline": roof, "cpu_baseline": base,
+                "e2e": {"value": e2e_per_solve, "unit": "s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line))
+    g.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,281 @@
+"""ctypes binding of include/exsaddle_b200.h (one Python method per C entry point)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libexsaddle_b200.so")
+
+MAT_A, MAT_A00, MAT_A01, MAT_A10, MAT_A11, MAT_MP, MAT_MG_LEVEL0 = 0, 1, 2, 3, 4, 5, 16
+ERR_NO_DEVICE = -6
+
+
+class XsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("exsaddle_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return _LIBPATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library. It must have been built (python -m exsaddle_b200.build); there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise ImportError("%s is missing: build it with `python exsaddle_b200/build.py` (nvcc, sm_100a). "
+                              "exsaddle_b200 has no CPU or PyTorch fallback." % _LIBPATH)
+        L = C.CDLL(_LIBPATH)
+        vp, i32p, i64p, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+        sig = {
+            "xsb_create": [C.POINTER(vp), C.c_int, C.c_int, C.c_int], "xsb_reset": [vp], "xsb_destroy": [C.POINTER(vp)],
+            "xsb_device_available": [], "xsb_set_option": [vp, C.c_char_p, C.c_char_p], "xsb_set_options": [vp, C.c_char_p],
+            "xsb_set_options_file": [vp, C.c_char_p], "xsb_options_left": [vp, C.c_char_p, C.c_int],
+            "xsb_assemble": [vp], "xsb_banner": [vp, C.c_char_p, C.c_int], "xsb_get_sizes": [vp, i64p],
+            "xsb_mat_get_info": [vp, C.c_int, i64p, i64p, i64p, C.POINTER(C.c_int)],
+            "xsb_mat_get_csr": [vp, C.c_int, i32p, i32p, dp], "xsb_mat_mult": [vp, C.c_int, dp, dp],
+            "xsb_mat_mult_dev": [vp, C.c_int, vp, vp], "xsb_mat_get_diagonal": [vp, C.c_int, dp],
+            "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
+            "xsb_ksp_setup": [vp], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
+            "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
+            "xsb_pc_schur_apply": [vp, dp, dp], "xsb_mg_restrict": [vp, C.c_int, dp, dp],
+            "xsb_mg_interpolate_add": [vp, C.c_int, dp, dp],
+            "xsb_ksp_get_iterations": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+            "xsb_ksp_get_history": [vp, dp, C.c_int, C.POINTER(C.c_int)],
+            "xsb_ksp_get_inner_iterations": [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)],
+            "xsb_ksp_get_chebyshev": [vp, C.c_int, dp, dp, dp, dp], "xsb_ksp_get_timing": [vp, dp, dp],
+            "xsb_ksp_get_counters": [vp, i64p], "xsb_diagnostics": [vp, dp, dp], "xsb_get_stream": [vp, C.POINTER(vp)],
+            "xsb_pattern_row": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, C.c_int],
+            "xsb_prealloc_total": [C.c_int, C.c_int, C.c_int, C.c_int],
+            "xsb_bc_list": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int],
+            "xsb_mg_level_dims": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
+            "xsb_slab_range": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        }
+        for name, args in sig.items():
+            f = getattr(L, name); f.argtypes = args; f.restype = C.c_int
+        L.xsb_last_error.argtypes = [vp]; L.xsb_last_error.restype = C.c_char_p
+        L.xsb_prealloc_total.restype = C.c_int64
+        L._symbols = list(sig) + ["xsb_last_error"]
+        _lib = L
+    return _lib
+
+
+def device_available():
+    return bool(lib().xsb_device_available())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+# ---- host-side index maps (no GPU) ------------------------------------------------------------------
+def pattern_row(nsd, mx, my, mz, row):
+    n = lib().xsb_pattern_row(nsd, mx, my, mz, row, None, 0)
+    if n < 0:
+        raise XsbError(n, "bad arguments")
+    cols = np.empty(n, np.int32)
+    lib().xsb_pattern_row(nsd, mx, my, mz, row, _ip(cols), n)
+    return cols
+
+
+def prealloc_total(nsd, mx, my, mz):
+    return int(lib().xsb_prealloc_total(nsd, mx, my, mz))
+
+
+def bc_list(nsd, lame, model, freeslip, mx, my, mz):
+    n = lib().xsb_bc_list(nsd, int(lame), model, int(freeslip), mx, my, mz, None, None, 0)
+    idx = np.empty(max(n, 1), np.int32); val = np.empty(max(n, 1))
+    lib().xsb_bc_list(nsd, int(lame), model, int(freeslip), mx, my, mz, _ip(idx), _dp(val), n)
+    return idx[:n], val[:n]
+
+
+def mg_level_dims(nsd, mx, my, mz, levels, level):
+    d = (C.c_int * 3)()
+    rc = lib().xsb_mg_level_dims(nsd, mx, my, mz, levels, level, d)
+    if rc:
+        raise XsbError(rc, "mesh cannot be coarsened to %d levels" % levels)
+    return tuple(d)
+
+
+def slab_range(mz, nranks, rank):
+    a, b = C.c_int(), C.c_int()
+    rc = lib().xsb_slab_range(mz, nranks, rank, C.byref(a), C.byref(b))
+    if rc:
+        raise XsbError(rc, "bad slab request")
+    return a.value, b.value
+
+
+class ExSaddle:
+    """One exSaddle{2d,3d}{,_lame} run on the GPU. `opts` is the reference's own option string."""
+
+    def __init__(self, opts="", nsd=3, lame=False, device=-1):
+        self.L = lib()
+        self.nsd, self.lame = nsd, bool(lame)
+        self.h = C.c_void_p()
+        rc = self.L.xsb_create(C.byref(self.h), nsd, int(lame), device)
+        if rc:
+            raise XsbError(rc, "xsb_create failed")
+        if opts:
+            self.set_options(opts)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.xsb_destroy(C.byref(self.h)); self.h = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc:
+            raise XsbError(rc, self.L.xsb_last_error(self.h).decode())
+
+    # options ------------------------------------------------------------------------------------------
+    def set_options(self, s):
+        self._chk(self.L.xsb_set_options(self.h, s.encode()))
+
+    def set_option(self, key, value=None):
+        self._chk(self.L.xsb_set_option(self.h, key.encode(), None if value is None else str(value).encode()))
+
+    def set_options_file(self, path):
+        self._chk(self.L.xsb_set_options_file(self.h, path.encode()))
+
+    def options_left(self):
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(self.L.xsb_options_left(self.h, buf, len(buf)))
+        return [l for l in buf.value.decode().split("\n") if l]
+
+    # FE set-up ----------------------------------------------------------------------------------------
+    def assemble(self):
+        self._chk(self.L.xsb_assemble(self.h))
+        sz = (C.c_int64 * 8)()
+        self._chk(self.L.xsb_get_sizes(self.h, sz))
+        (self.n, self.nu, self.np_, self.nnz, self.prealloc, self.nel, self.nbc, self.mnnz) = [int(v) for v in sz]
+        return self
+
+    def banner(self):
+        buf = C.create_string_buffer(4096)
+        self._chk(self.L.xsb_banner(self.h, buf, len(buf)))
+        return buf.value.decode()
+
+    def mat_info(self, which):
+        r, c_, z, bs = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        self._chk(self.L.xsb_mat_get_info(self.h, which, C.byref(r), C.byref(c_), C.byref(z), C.byref(bs)))
+        return r.value, c_.value, z.value, bs.value
+
+    def mat_csr(self, which, values=True, pattern=True):
+        r, c_, z, _ = self.mat_info(which)
+        ia = np.empty(r + 1, np.int32); ja = np.empty(z, np.int32) if pattern else None
+        a = np.empty(z) if values else None
+        self._chk(self.L.xsb_mat_get_csr(self.h, which, _ip(ia), _ip(ja) if pattern else None, _dp(a) if values else None))
+        return ia, ja, a, (r, c_)
+
+    def mat_mult(self, which, x):
+        r, c_, _, _ = self.mat_info(which)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (c_,)
+        y = np.empty(r)
+        self._chk(self.L.xsb_mat_mult(self.h, which, _dp(x), _dp(y)))
+        return y
+
+    def mat_mult_dev(self, which, x_ptr, y_ptr):
+        self._chk(self.L.xsb_mat_mult_dev(self.h, which, C.c_void_p(x_ptr), C.c_void_p(y_ptr)))
+
+    def mat_diagonal(self, which):
+        r = self.mat_info(which)[0]; d = np.empty(r)
+        self._chk(self.L.xsb_mat_get_diagonal(self.h, which, _dp(d))); return d
+
+    def rhs(self):
+        F = np.empty(self.n); self._chk(self.L.xsb_vec_get_rhs(self.h, _dp(F))); return F
+
+    def bc(self):
+        idx = np.empty(max(self.nbc, 1), np.int32); val = np.empty(max(self.nbc, 1))
+        self._chk(self.L.xsb_get_bc(self.h, _ip(idx), _dp(val)))
+        return idx[:self.nbc], val[:self.nbc]
+
+    def coeff_qp(self, slot):
+        out = np.empty(self.nel * (27 if self.nsd == 3 else 9))
+        self._chk(self.L.xsb_get_coeff_qp(self.h, slot, _dp(out))); return out
+
+    # solver -------------------------------------------------------------------------------------------
+    def ksp_setup(self):
+        self._chk(self.L.xsb_ksp_setup(self.h)); return self
+
+    def solve(self, b=None):
+        x = np.empty(self.n)
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.float64); bp = _dp(b)
+        self._chk(self.L.xsb_ksp_solve(self.h, bp, _dp(x)))
+        return x
+
+    def solve_dev(self, b_ptr, x_ptr):
+        self._chk(self.L.xsb_ksp_solve_dev(self.h, C.c_void_p(b_ptr) if b_ptr else None, C.c_void_p(x_ptr)))
+
+    def pc_apply(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64); z = np.empty(self.n)
+        self._chk(self.L.xsb_pc_apply(self.h, _dp(r), _dp(z))); return z
+
+    def pc_mg_apply(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64); x = np.empty(self.nu)
+        self._chk(self.L.xsb_pc_mg_apply(self.h, _dp(b), _dp(x))); return x
+
+    def pc_schur_apply(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64); x = np.empty(self.np_)
+        self._chk(self.L.xsb_pc_schur_apply(self.h, _dp(b), _dp(x))); return x
+
+    def mg_restrict(self, lc, rf):
+        nc = self.mat_info(MAT_MG_LEVEL0 + lc)[0]
+        rf = np.ascontiguousarray(rf, dtype=np.float64); bc = np.empty(nc)
+        self._chk(self.L.xsb_mg_restrict(self.h, lc, _dp(rf), _dp(bc))); return bc
+
+    def mg_interpolate_add(self, lc, xc, xf):
+        xc = np.ascontiguousarray(xc, dtype=np.float64); xf = np.array(xf, dtype=np.float64)
+        self._chk(self.L.xsb_mg_interpolate_add(self.h, lc, _dp(xc), _dp(xf))); return xf
+
+    def iterations(self):
+        its, reason = C.c_int(), C.c_int()
+        self._chk(self.L.xsb_ksp_get_iterations(self.h, C.byref(its), C.byref(reason)))
+        return its.value, reason.value
+
+    def history(self):
+        n = C.c_int(); h = np.empty(20000)
+        self._chk(self.L.xsb_ksp_get_history(self.h, _dp(h), len(h), C.byref(n)))
+        return h[:n.value].copy()
+
+    def inner_iterations(self):
+        n = C.c_int(); a = (C.c_int * 20000)()
+        self._chk(self.L.xsb_ksp_get_inner_iterations(self.h, a, 20000, C.byref(n)))
+        return [a[i] for i in range(n.value)]
+
+    def chebyshev(self, level):
+        v = [C.c_double() for _ in range(4)]
+        self._chk(self.L.xsb_ksp_get_chebyshev(self.h, level, *[C.byref(t) for t in v]))
+        return tuple(t.value for t in v)
+
+    def timing(self):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self.L.xsb_ksp_get_timing(self.h, C.byref(a), C.byref(b))); return a.value, b.value
+
+    def counters(self):
+        out = (C.c_int64 * 8)()
+        self._chk(self.L.xsb_ksp_get_counters(self.h, out))
+        return {"a00_spmv": out[0], "a_spmv": out[1], "launches": out[2], "a00_avg_ns": out[3],
+                "a00_by_mode": [out[4], out[5], out[6], out[7]]}
+
+    def stream(self):
+        p = C.c_void_p()
+        self._chk(self.L.xsb_get_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def diagnostics(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64); out = np.empty(5 * self.nsd + 5)
+        self._chk(self.L.xsb_diagnostics(self.h, _dp(x), _dp(out))); return out

@@ -1,0 +1,216 @@
+// xsb.h -- internal structures of the B200 exSaddle library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+#include "../../include/exsaddle_b200.h"
+
+#define XSB_MAX_LEVELS 10   // MG_DEPTH, exSaddle.h:24
+#define XSB_NSLOT 6         // coefficient slots at a quadrature point
+enum { C_ETA = 0, C_FU0 = 1, C_FU1 = 2, C_FU2 = 3, C_FP = 4, C_LAM = 5 };
+enum { BC_SOLCX = 0, BC_FIXEDBASE, BC_COMPRESSION, BC_COMPRESSION2, BC_MMS1 };
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#else
+#define HD inline
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// Lattice description shared by host and device code.
+struct Lattice {
+  int nsd;
+  int mx, my, mz;          // elements (mz = 1 in 2-D)
+  int NX, NY, NZ;          // velocity nodes
+  int PX, PY, PZ;          // pressure nodes
+  int64_t nun, npn, nu, np, n, nel;
+  double hu[3];            // velocity node spacing
+};
+
+// Coupling ranges along one direction. i = node coordinate, N = nodes in that direction.
+// velocity node -> velocity nodes: +-2 from an element-corner (even) node, +-1 from a mid (odd) node.
+HD void range_uu(int i, int N, int &lo, int &hi) { if (i & 1) { lo = i - 1; hi = i + 1; } else { lo = i - 2 < 0 ? 0 : i - 2; hi = i + 2 > N - 1 ? N - 1 : i + 2; } }
+// velocity node -> pressure nodes
+HD void range_up(int i, int P, int &lo, int &hi) { if (i & 1) { lo = (i - 1) >> 1; hi = (i + 1) >> 1; } else { int p = i >> 1; lo = p - 1 < 0 ? 0 : p - 1; hi = p + 1 > P - 1 ? P - 1 : p + 1; } }
+// pressure node -> velocity nodes
+HD void range_pu(int p, int N, int &lo, int &hi) { lo = 2 * p - 2 < 0 ? 0 : 2 * p - 2; hi = 2 * p + 2 > N - 1 ? N - 1 : 2 * p + 2; }
+// pressure node -> pressure nodes (also every coarse MG level: 27-point box)
+HD void range_pp(int p, int P, int &lo, int &hi) { lo = p - 1 < 0 ? 0 : p - 1; hi = p + 1 > P - 1 ? P - 1 : p + 1; }
+
+// A "box pattern" block matrix on a node lattice: block row of node (i,j,k) couples to the nodes of the box
+// [lo,hi] per direction; q2 = 1 uses range_uu (finest velocity level), q2 = 0 uses range_pp (27-point).
+struct BoxPattern { int nx, ny, nz, q2; };
+HD void box_range(const BoxPattern &p, int c, int n, int &lo, int &hi) { if (p.q2) range_uu(c, n, lo, hi); else range_pp(c, n, lo, hi); }
+
+// Column boxes of one AIJ row (velocity-node row or pressure-node row): velocity-node box and pressure-node box.
+struct RowBox { int ulo[3], uhi[3], plo[3], phi[3]; int ncu, ncp; };
+HD void row_box_u(const Lattice &L, int i, int j, int k, RowBox &b)
+{
+  range_uu(i, L.NX, b.ulo[0], b.uhi[0]); range_uu(j, L.NY, b.ulo[1], b.uhi[1]); range_uu(k, L.NZ, b.ulo[2], b.uhi[2]);
+  range_up(i, L.PX, b.plo[0], b.phi[0]); range_up(j, L.PY, b.plo[1], b.phi[1]); range_up(k, L.PZ, b.plo[2], b.phi[2]);
+  b.ncu = (b.uhi[0] - b.ulo[0] + 1) * (b.uhi[1] - b.ulo[1] + 1) * (b.uhi[2] - b.ulo[2] + 1);
+  b.ncp = (b.phi[0] - b.plo[0] + 1) * (b.phi[1] - b.plo[1] + 1) * (b.phi[2] - b.plo[2] + 1);
+}
+HD void row_box_p(const Lattice &L, int i, int j, int k, RowBox &b)
+{
+  range_pu(i, L.NX, b.ulo[0], b.uhi[0]); range_pu(j, L.NY, b.ulo[1], b.uhi[1]); range_pu(k, L.NZ, b.ulo[2], b.uhi[2]);
+  range_pp(i, L.PX, b.plo[0], b.phi[0]); range_pp(j, L.PY, b.plo[1], b.phi[1]); range_pp(k, L.PZ, b.plo[2], b.phi[2]);
+  b.ncu = (b.uhi[0] - b.ulo[0] + 1) * (b.uhi[1] - b.ulo[1] + 1) * (b.uhi[2] - b.ulo[2] + 1);
+  b.ncp = (b.phi[0] - b.plo[0] + 1) * (b.phi[1] - b.plo[1] + 1) * (b.phi[2] - b.plo[2] + 1);
+}
+// slot of velocity node (ii,jj,kk) / pressure node inside a row's box (ascending node index order)
+HD int box_upos(const RowBox &b, int ii, int jj, int kk) { return ((kk - b.ulo[2]) * (b.uhi[1] - b.ulo[1] + 1) + (jj - b.ulo[1])) * (b.uhi[0] - b.ulo[0] + 1) + (ii - b.ulo[0]); }
+HD int box_ppos(const RowBox &b, int ii, int jj, int kk) { return ((kk - b.plo[2]) * (b.phi[1] - b.plo[1] + 1) + (jj - b.plo[1])) * (b.phi[0] - b.plo[0] + 1) + (ii - b.plo[0]); }
+// AIJ row -> box; returns 1 for a velocity row (comp in *a) and 0 for a pressure row
+HD int row_to_box(const Lattice &L, int64_t row, RowBox &b, int *comp)
+{
+  if (row < L.nu) { int64_t nd = row / L.nsd; *comp = (int)(row - nd * L.nsd); int i = (int)(nd % L.NX), j = (int)((nd / L.NX) % L.NY), k = (int)(nd / ((int64_t)L.NX * L.NY)); row_box_u(L, i, j, k, b); return 1; }
+  int64_t nd = row - L.nu; *comp = 0; int i = (int)(nd % L.PX), j = (int)((nd / L.PX) % L.PY), k = (int)(nd / ((int64_t)L.PX * L.PY)); row_box_p(L, i, j, k, b); return 0;
+}
+// block-row box of a BoxPattern lattice matrix
+HD int box_size(const BoxPattern &p, int i, int j, int k)
+{ int l0, h0, l1, h1, l2, h2; box_range(p, i, p.nx, l0, h0); box_range(p, j, p.ny, l1, h1); box_range(p, k, p.nz, l2, h2); return (h0 - l0 + 1) * (h1 - l1 + 1) * (h2 - l2 + 1); }
+// slot of node (gi,gj,gk) in the block row of node (i,j,k), or -1 when outside the box
+HD int box_slot(const BoxPattern &p, int i, int j, int k, int gi, int gj, int gk)
+{
+  int l0, h0, l1, h1, l2, h2; box_range(p, i, p.nx, l0, h0); box_range(p, j, p.ny, l1, h1); box_range(p, k, p.nz, l2, h2);
+  if (gi < l0 || gi > h0 || gj < l1 || gj > h1 || gk < l2 || gk > h2) return -1;
+  return ((gk - l2) * (h1 - l1 + 1) + (gj - l1)) * (h0 - l0 + 1) + (gi - l0);
+}
+
+struct Csr  { int n = 0, m = 0; int64_t nnz = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; };
+// BAIJ: block rows = lattice nodes, blocks bs x bs stored row-major, block columns ascending.
+struct Baij { int nb = 0, bs = 0; int64_t nblk = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; BoxPattern pat{0, 0, 0, 0}; };
+
+struct Level {
+  int nx = 0, ny = 0, nz = 0;
+  Baij A; bool owns_A = false;
+  double *idiag = nullptr;
+  double emin = 0, emax = 0, emin_est = NAN, emax_est = NAN;
+  double *x = nullptr, *b = nullptr, *r = nullptr, *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
+  double *inv = nullptr;      // dense inverse of the coarsest operator
+};
+
+struct Options {
+  std::map<std::string, std::string> kv;
+  std::set<std::string> used;
+  bool has(const std::string &k) { if (kv.count(k)) { used.insert(k); return true; } return false; }
+  std::string str(const std::string &k, const std::string &d) { if (has(k)) return kv[k]; return d; }
+  double real(const std::string &k, double d) { if (has(k)) return atof(kv[k].c_str()); return d; }
+  int integer(const std::string &k, int d) { if (has(k)) return atoi(kv[k].c_str()); return d; }
+  bool flag(const std::string &k) { if (!has(k)) return false; const std::string &v = kv[k]; return v.empty() || v == "1" || v == "true" || v == "yes"; }
+};
+
+struct Model {   // resolved model parameters (models.c static option blocks)
+  int model = -1, bc_type = BC_SOLCX;
+  double c0 = 1, c1 = 1, lam0 = 1, lam1 = 1, rad = 0, cx = 0.5, cy = 0.5, cz = 0.5, xc = 0.5, size_x = 1;
+  int nsink = 3, nz = 1, freeslip = 0;
+};
+
+struct SolverOpts {
+  int ksp_type = 0;      // 0 gmres 1 fgmres
+  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf)
+  int right = 0;
+  double rtol = 1e-5, atol = 1e-50, dtol = 1e4; int max_it = 10000, restart = 30;
+  double u_rtol = 1e-5; int u_max_it = 10000, u_restart = 30;
+  int mg_levels = 1, cheb_its = 2; double esteig[4] = {0, 0.1, 0, 1.1}; int esteig_steps = 10, noise = 0;
+  int n_cheb_fixed = 0; double cheb_emin[XSB_MAX_LEVELS], cheb_emax[XSB_MAX_LEVELS];
+  int p_pc = 0;          // 0 ilu0 (bjacobi) 1 jacobi
+  int time_kernels = 0;
+};
+
+struct xsb_ctx_s {
+  int nsd = 3, lame = 0, device = 0;
+  bool have_device = false;
+  cudaStream_t stream = nullptr;
+  std::string err, banner;
+  Options opt;
+  Lattice lat{};
+  Model mdl;
+  SolverOpts so;
+  bool assembled = false, ksp_ready = false;
+  // FE data (device)
+  double *coeff = nullptr;       // [slot][nel*nqp]
+  double *coeff_nodal = nullptr; // [slot][npn]
+  int nbc = 0; int *bc_idx = nullptr; double *bc_val = nullptr; unsigned char *isbc = nullptr;
+  Csr A, A01, A10, A11, Mp;
+  Baij A00;
+  double *F = nullptr;
+  double *idiagA = nullptr;
+  // solver state
+  int nlev = 0; Level lev[XSB_MAX_LEVELS];
+  double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr; int ilu_nlvl = 0;
+  std::vector<int> ilu_lvl_off_h;
+  std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
+  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr;
+  double *red = nullptr;      // device reduction scratch
+  double *red_h = nullptr;    // pinned host mirror
+  double *scal = nullptr;     // device scalars (dot results consumed by kernels)
+  // results
+  int its = 0, reason = 0; std::vector<double> hist; std::vector<int> inner_its;
+  float setup_ms = 0, solve_ms = 0;
+  int64_t n_a00 = 0, n_a = 0, n_launch = 0, solve_launches = 0; double a00_ns_sum = 0; int64_t a00_timed = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  std::vector<cudaEvent_t> evpool; size_t ev_used = 0;   // event pairs around fine-level A00 launches (-xsb_time_kernels)
+  int64_t a00_mode[4] = {0, 0, 0, 0};                    // fine-level A00 launches per epilogue mode
+  std::vector<void *> allocs;   // every device allocation, for xsb_reset
+  void *fe_tables = nullptr;    // FeTables on the device
+};
+
+int xsb_fail(xsb_ctx c, int code, const char *fmt, ...);
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return xsb_fail(c, XSB_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define XSB_CHK(call) do { int rc_ = (call); if (rc_) return rc_; } while (0)
+#define KERNEL_OK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return xsb_fail(c, XSB_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); c->n_launch++; } while (0)
+
+template <class T> int dev_alloc(xsb_ctx c, T **p, size_t n);
+int dev_free_all(xsb_ctx c);
+
+// ---- xsb_fe.cu
+int fe_resolve_model(xsb_ctx c);
+int fe_assemble(xsb_ctx c);
+// ---- xsb_spmv.cu
+enum { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_CHEB_FIRST = 2, EPI_CHEB = 3 };
+struct Epilogue { int mode = EPI_PLAIN; const double *b = nullptr, *idiag = nullptr, *pk = nullptr, *pkm1 = nullptr; double s0 = 0, s1 = 0, s2 = 0; };
+int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y);
+int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);
+int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);   // counted (+ timed) fine-level launch
+int spmv_collect_timing(xsb_ctx c);
+// ---- xsb_vec.cu
+int vec_set(xsb_ctx c, int64_t n, double a, double *x);
+int vec_copy(xsb_ctx c, int64_t n, const double *x, double *y);
+int vec_axpy(xsb_ctx c, int64_t n, double a, const double *x, double *y);            // y += a x
+int vec_aypx(xsb_ctx c, int64_t n, double a, const double *x, double *y);            // y = x + a y
+int vec_scale(xsb_ctx c, int64_t n, double a, double *x);
+int vec_pmult(xsb_ctx c, int64_t n, const double *d, const double *x, double *y);    // y = d .* x
+int vec_waxpy(xsb_ctx c, int64_t n, double a, const double *x, const double *y, double *w); // w = y + a x
+int vec_mdot(xsb_ctx c, int64_t n, const double *w, double *const *V, int k, bool with_norm, double *out_dev); // out[j] = w.V[j], out[k] = w.w
+int vec_maxpy_dev(xsb_ctx c, int64_t n, double *w, double *const *V, int k, const double *coef_dev, double sign); // w += sign * sum coef[j] V[j]
+int vec_maxpy_host(xsb_ctx c, int64_t n, double *w, double *const *V, int k, const double *coef_host);
+int vec_scale_by_inv_sqrt(xsb_ctx c, int64_t n, double *w, const double *nrm2_dev);  // w /= sqrt(*nrm2)
+int vec_gcr_update(xsb_ctx c, int64_t n, const double *dots_dev /* [r.v, v.v] */, double *v, double *s, double *x, double *r, double *rnorm2_dev);
+int vec_fetch(xsb_ctx c, const double *dev, int n, double *host);   // sync copy of n scalars
+int vec_diagnostics(xsb_ctx c, const double *x, double *out);
+int vec_rander48(xsb_ctx c, int64_t n, int interval, double *x);
+// ---- xsb_mg.cu
+int mg_setup(xsb_ctx c);
+int mg_vcycle(xsb_ctx c, const double *b, double *x);
+int mg_restrict(xsb_ctx c, const Level &F, const Level &C, const double *rf, double *bc);
+int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, double *xf);
+int baij_to_csr_host(xsb_ctx c, const Baij &A, int32_t *ia, int32_t *ja, double *a);
+int baij_diag_inv(xsb_ctx c, const Baij &A, double *idiag);
+// ---- xsb_ilu.cu
+int ilu_setup(xsb_ctx c);
+int ilu_apply(xsb_ctx c, const double *b, double *x);
+// ---- xsb_ksp.cu
+int ksp_setup(xsb_ctx c);
+int ksp_solve(xsb_ctx c, const double *b_dev, double *x_dev);
+int pc_apply(xsb_ctx c, const double *r, double *z, int *inner);
+int hess_eig(int n, const double *H, int ldh, double *wr, double *wi);
+int csr_diag_inv(xsb_ctx c, const Csr &A, double *idiag);

@@ -1,0 +1,521 @@
+// xsb_api.cu -- the C ABI (include/exsaddle_b200.h): handle lifecycle, options database, host<->device
+// staging for the host-pointer entry points, and the host-side integer index maps.
+#include "xsb.h"
+#include <cstdarg>
+#include <fstream>
+#include <sstream>
+
+int xsb_fail(xsb_ctx c, int code, const char *fmt, ...)
+{
+  char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+template <class T> int dev_alloc(xsb_ctx c, T **p, size_t n)
+{
+  void *q = nullptr; if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return xsb_fail(c, XSB_ERR_MEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  c->allocs.push_back(q); *p = (T *)q;
+  return 0;
+}
+template int dev_alloc<double>(xsb_ctx, double **, size_t);
+template int dev_alloc<int>(xsb_ctx, int **, size_t);
+template int dev_alloc<char>(xsb_ctx, char **, size_t);
+template int dev_alloc<unsigned char>(xsb_ctx, unsigned char **, size_t);
+
+int dev_free_all(xsb_ctx c)
+{
+  for (void *p : c->allocs) cudaFree(p);
+  c->allocs.clear();
+  return 0;
+}
+
+extern "C" {
+
+int xsb_device_available(void)
+{
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0;
+}
+
+int xsb_create(xsb_ctx *out, int nsd, int lame, int device)
+{
+  if (!out) return XSB_ERR_ARG;
+  *out = nullptr;
+  if (nsd != 2 && nsd != 3) return XSB_ERR_ARG;   // exSaddle.h:7-9
+  xsb_ctx c = new xsb_ctx_s();
+  c->nsd = nsd; c->lame = lame ? 1 : 0;
+  *out = c;
+  if (!xsb_device_available()) { c->have_device = false; c->err = "no CUDA device: exsaddle_b200 has no CPU path"; return XSB_OK; }
+  if (device >= 0) { CUDA_OK(cudaSetDevice(device)); c->device = device; } else CUDA_OK(cudaGetDevice(&c->device));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&c->ev0)); CUDA_OK(cudaEventCreate(&c->ev1)); CUDA_OK(cudaEventCreate(&c->evk0)); CUDA_OK(cudaEventCreate(&c->evk1));
+  c->have_device = true;
+  return XSB_OK;
+}
+
+#define NEED_DEVICE(c) do { if (!(c)) return XSB_ERR_ARG; if (!(c)->have_device) return xsb_fail(c, XSB_ERR_NO_DEVICE, "no CUDA device: exsaddle_b200 has no CPU path"); cudaSetDevice((c)->device); } while (0)
+
+int xsb_reset(xsb_ctx c)
+{
+  if (!c) return XSB_ERR_ARG;
+  if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
+  Options opt = c->opt; int nsd = c->nsd, lame = c->lame, device = c->device; bool hd = c->have_device;
+  cudaStream_t st = c->stream; cudaEvent_t e0 = c->ev0, e1 = c->ev1, k0 = c->evk0, k1 = c->evk1;
+  *c = xsb_ctx_s();
+  c->opt = opt; c->opt.used.clear(); c->nsd = nsd; c->lame = lame; c->device = device; c->have_device = hd;
+  c->stream = st; c->ev0 = e0; c->ev1 = e1; c->evk0 = k0; c->evk1 = k1;
+  return XSB_OK;
+}
+
+int xsb_destroy(xsb_ctx *pc)
+{
+  if (!pc || !*pc) return XSB_OK;
+  xsb_ctx c = *pc;
+  xsb_reset(c);
+  if (c->have_device) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1); cudaStreamDestroy(c->stream); }
+  delete c; *pc = nullptr;
+  return XSB_OK;
+}
+
+const char *xsb_last_error(xsb_ctx c) { return c ? c->err.c_str() : "null handle"; }
+
+// ---------------------------------------------------------------- options
+static bool looks_like_value(const std::string &t)
+{
+  if (t.empty() || t[0] != '-') return true;
+  if (t.size() > 1 && (isdigit((unsigned char)t[1]) || t[1] == '.')) return true;   // negative number
+  return false;
+}
+
+int xsb_set_option(xsb_ctx c, const char *key, const char *value)
+{
+  if (!c || !key) return XSB_ERR_ARG;
+  std::string k = key; if (!k.empty() && k[0] == '-') k = k.substr(1);
+  if (k.empty()) return xsb_fail(c, XSB_ERR_ARG, "empty option name");
+  if (k == "options_file") return xsb_set_options_file(c, value ? value : "");
+  c->opt.kv[k] = value ? value : "";
+  c->ksp_ready = false;
+  return XSB_OK;
+}
+
+int xsb_set_options(xsb_ctx c, const char *cmdline)
+{
+  if (!c || !cmdline) return XSB_ERR_ARG;
+  std::istringstream in(cmdline); std::string line;
+  while (std::getline(in, line)) {
+    size_t h = line.find('#'); if (h != std::string::npos) line = line.substr(0, h);
+    std::istringstream ls(line); std::vector<std::string> tok; std::string t;
+    while (ls >> t) tok.push_back(t);
+    for (size_t i = 0; i < tok.size();) {
+      if (tok[i][0] != '-' || looks_like_value(tok[i])) { ++i; continue; }
+      if (i + 1 < tok.size() && looks_like_value(tok[i + 1])) { XSB_CHK(xsb_set_option(c, tok[i].c_str(), tok[i + 1].c_str())); i += 2; }
+      else { XSB_CHK(xsb_set_option(c, tok[i].c_str(), nullptr)); i += 1; }
+    }
+  }
+  return XSB_OK;
+}
+
+int xsb_set_options_file(xsb_ctx c, const char *path)
+{
+  if (!c || !path) return XSB_ERR_ARG;
+  std::ifstream f(path);
+  if (!f) return xsb_fail(c, XSB_ERR_ARG, "cannot open options file %s", path);
+  std::stringstream ss; ss << f.rdbuf();
+  // command-line options win over file options (PETSc inserts the file first)
+  std::map<std::string, std::string> keep = c->opt.kv;
+  XSB_CHK(xsb_set_options(c, ss.str().c_str()));
+  for (auto &kv : keep) c->opt.kv[kv.first] = kv.second;
+  return XSB_OK;
+}
+
+int xsb_options_left(xsb_ctx c, char *buf, int buflen)
+{
+  if (!c || !buf || buflen < 1) return XSB_ERR_ARG;
+  std::string s;
+  for (auto &kv : c->opt.kv) if (!c->opt.used.count(kv.first)) { s += "-" + kv.first; if (!kv.second.empty()) s += " " + kv.second; s += "\n"; }
+  snprintf(buf, buflen, "%s", s.c_str());
+  return XSB_OK;
+}
+
+// ---------------------------------------------------------------- set-up
+int xsb_assemble(xsb_ctx c)
+{
+  NEED_DEVICE(c);
+  if (c->assembled) { Options keep = c->opt; XSB_CHK(xsb_reset(c)); c->opt = keep; }
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  int rc = fe_assemble(c);
+  if (rc) return rc;
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream)); CUDA_OK(cudaEventSynchronize(c->ev1));
+  return XSB_OK;
+}
+
+int xsb_banner(xsb_ctx c, char *buf, int buflen)
+{
+  if (!c || !buf || buflen < 1) return XSB_ERR_ARG;
+  if (c->banner.empty()) { int rc = fe_resolve_model(c); if (rc) return rc; }
+  snprintf(buf, buflen, "%s", c->banner.c_str());
+  return XSB_OK;
+}
+
+int xsb_get_sizes(xsb_ctx c, int64_t out[8])
+{
+  if (!c || !out) return XSB_ERR_ARG;
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_get_sizes before xsb_assemble");
+  const Lattice &L = c->lat;
+  out[0] = L.n; out[1] = L.nu; out[2] = L.np; out[3] = c->A.nnz; out[4] = xsb_prealloc_total(c->nsd, L.mx, L.my, L.mz);
+  out[5] = L.nel; out[6] = c->nbc; out[7] = c->Mp.nnz;
+  return XSB_OK;
+}
+
+static int pick_csr(xsb_ctx c, int which, const Csr **S, const Baij **B)
+{
+  *S = nullptr; *B = nullptr;
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "matrix requested before xsb_assemble");
+  switch (which) {
+  case XSB_MAT_A: *S = &c->A; return 0;
+  case XSB_MAT_A00: *B = &c->A00; return 0;
+  case XSB_MAT_A01: *S = &c->A01; return 0;
+  case XSB_MAT_A10: *S = &c->A10; return 0;
+  case XSB_MAT_A11: *S = &c->A11; return 0;
+  case XSB_MAT_MP: *S = &c->Mp; return 0;
+  default:
+    if (which >= XSB_MAT_MG_LEVEL0 && which < XSB_MAT_MG_LEVEL0 + c->nlev) { *B = &c->lev[which - XSB_MAT_MG_LEVEL0].A; return 0; }
+    return xsb_fail(c, XSB_ERR_ARG, "unknown matrix id %d", which);
+  }
+}
+
+int xsb_mat_get_info(xsb_ctx c, int which, int64_t *rows, int64_t *cols, int64_t *nnz, int *bs)
+{
+  NEED_DEVICE(c);
+  const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
+  if (S) { if (rows) *rows = S->n; if (cols) *cols = S->m; if (nnz) *nnz = S->nnz; if (bs) *bs = 1; }
+  else { if (rows) *rows = (int64_t)B->nb * B->bs; if (cols) *cols = (int64_t)B->nb * B->bs; if (nnz) *nnz = B->nblk * B->bs * B->bs; if (bs) *bs = B->bs; }
+  return XSB_OK;
+}
+
+int xsb_mat_get_csr(xsb_ctx c, int which, int32_t *ia, int32_t *ja, double *a)
+{
+  NEED_DEVICE(c);
+  const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (S) {
+    if (ia) CUDA_OK(cudaMemcpy(ia, S->ia, sizeof(int) * ((size_t)S->n + 1), cudaMemcpyDeviceToHost));
+    if (ja) CUDA_OK(cudaMemcpy(ja, S->ja, sizeof(int) * (size_t)S->nnz, cudaMemcpyDeviceToHost));
+    if (a) CUDA_OK(cudaMemcpy(a, S->a, sizeof(double) * (size_t)S->nnz, cudaMemcpyDeviceToHost));
+    return XSB_OK;
+  }
+  return baij_to_csr_host(c, *B, ia, ja, a);
+}
+
+int xsb_mat_mult_dev(xsb_ctx c, int which, const double *x, double *y)
+{
+  NEED_DEVICE(c);
+  const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
+  if (S) return spmv_csr(c, *S, x, y);
+  Epilogue ep; return spmv_baij(c, *B, x, y, ep);
+}
+
+int xsb_mat_mult(xsb_ctx c, int which, const double *x, double *y)
+{
+  NEED_DEVICE(c);
+  int64_t rows, cols; XSB_CHK(xsb_mat_get_info(c, which, &rows, &cols, nullptr, nullptr));
+  double *dx = nullptr, *dy = nullptr;
+  CUDA_OK(cudaMalloc(&dx, sizeof(double) * cols)); CUDA_OK(cudaMalloc(&dy, sizeof(double) * rows));
+  CUDA_OK(cudaMemcpyAsync(dx, x, sizeof(double) * cols, cudaMemcpyHostToDevice, c->stream));
+  int rc = xsb_mat_mult_dev(c, which, dx, dy);
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(y, dy, sizeof(double) * rows, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = xsb_fail(c, XSB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
+int xsb_mat_get_diagonal(xsb_ctx c, int which, double *d)
+{
+  NEED_DEVICE(c);
+  int64_t rows, cols, nnz; XSB_CHK(xsb_mat_get_info(c, which, &rows, &cols, &nnz, nullptr));
+  std::vector<int32_t> ia(rows + 1), ja(nnz); std::vector<double> a(nnz);
+  XSB_CHK(xsb_mat_get_csr(c, which, ia.data(), ja.data(), a.data()));
+  for (int64_t i = 0; i < rows; ++i) { d[i] = 0.0; for (int k = ia[i]; k < ia[i + 1]; ++k) if (ja[k] == i) d[i] = a[k]; }
+  return XSB_OK;
+}
+
+int xsb_vec_get_rhs(xsb_ctx c, double *F)
+{
+  NEED_DEVICE(c);
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_vec_get_rhs before xsb_assemble");
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemcpy(F, c->F, sizeof(double) * c->lat.n, cudaMemcpyDeviceToHost));
+  return XSB_OK;
+}
+
+int xsb_get_bc(xsb_ctx c, int32_t *idx, double *val)
+{
+  NEED_DEVICE(c);
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_get_bc before xsb_assemble");
+  if (c->nbc == 0) return XSB_OK;
+  if (idx) CUDA_OK(cudaMemcpy(idx, c->bc_idx, sizeof(int) * c->nbc, cudaMemcpyDeviceToHost));
+  if (val) CUDA_OK(cudaMemcpy(val, c->bc_val, sizeof(double) * c->nbc, cudaMemcpyDeviceToHost));
+  return XSB_OK;
+}
+
+int xsb_get_coeff_qp(xsb_ctx c, int slot, double *out)
+{
+  NEED_DEVICE(c);
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_get_coeff_qp before xsb_assemble");
+  if (slot < 0 || slot >= XSB_NSLOT) return xsb_fail(c, XSB_ERR_ARG, "coefficient slot %d", slot);
+  const int64_t nq = c->lat.nel * (c->nsd == 3 ? 27 : 9);
+  CUDA_OK(cudaMemcpy(out, c->coeff + (int64_t)slot * nq, sizeof(double) * nq, cudaMemcpyDeviceToHost));
+  return XSB_OK;
+}
+
+// ---------------------------------------------------------------- solver
+int xsb_ksp_setup(xsb_ctx c) { NEED_DEVICE(c); return ksp_setup(c); }
+
+int xsb_ksp_solve_dev(xsb_ctx c, const double *b, double *x) { NEED_DEVICE(c); return ksp_solve(c, b, x); }
+
+int xsb_ksp_solve(xsb_ctx c, const double *b, double *x)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready) return xsb_fail(c, XSB_ERR_ORDER, "xsb_ksp_solve called before xsb_ksp_setup");
+  const int64_t n = c->lat.n;
+  if (b) CUDA_OK(cudaMemcpyAsync(c->bdev, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  XSB_CHK(ksp_solve(c, b ? c->bdev : nullptr, c->xdev));
+  CUDA_OK(cudaMemcpyAsync(x, c->xdev, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return XSB_OK;
+}
+
+int xsb_pc_apply_dev(xsb_ctx c, const double *r, double *z) { NEED_DEVICE(c); if (!c->ksp_ready) return xsb_fail(c, XSB_ERR_ORDER, "PC not set up"); return pc_apply(c, r, z, nullptr); }
+
+static int staged(xsb_ctx c, int64_t nin, int64_t nout, const double *hin, double *hout, int (*fn)(xsb_ctx, const double *, double *))
+{
+  double *di = nullptr, *dout = nullptr;
+  CUDA_OK(cudaMalloc(&di, sizeof(double) * nin)); CUDA_OK(cudaMalloc(&dout, sizeof(double) * nout));
+  CUDA_OK(cudaMemcpyAsync(di, hin, sizeof(double) * nin, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemsetAsync(dout, 0, sizeof(double) * nout, c->stream));
+  int rc = fn(c, di, dout);
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(hout, dout, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = xsb_fail(c, XSB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  cudaFree(di); cudaFree(dout);
+  return rc;
+}
+
+int xsb_pc_apply(xsb_ctx c, const double *r, double *z)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready) return xsb_fail(c, XSB_ERR_ORDER, "PC not set up");
+  return staged(c, c->lat.n, c->lat.n, r, z, [](xsb_ctx cc, const double *a, double *b) { return pc_apply(cc, a, b, nullptr); });
+}
+int xsb_pc_mg_apply(xsb_ctx c, const double *b, double *x)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready || c->so.pc_type != 2) return xsb_fail(c, XSB_ERR_ORDER, "PCMG not set up");
+  return staged(c, c->lat.nu, c->lat.nu, b, x, [](xsb_ctx cc, const double *a, double *bb) { return mg_vcycle(cc, a, bb); });
+}
+int xsb_pc_schur_apply(xsb_ctx c, const double *b, double *x)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready || c->so.pc_type != 2) return xsb_fail(c, XSB_ERR_ORDER, "fieldsplit PC not set up");
+  return staged(c, c->lat.np, c->lat.np, b, x, [](xsb_ctx cc, const double *a, double *bb) {
+    if (cc->so.p_pc == 0) return ilu_apply(cc, a, bb);
+    return vec_pmult(cc, cc->lat.np, cc->mp_idiag, a, bb); });
+}
+
+int xsb_mg_restrict(xsb_ctx c, int lc, const double *rf, double *bc)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready || lc < 0 || lc + 1 >= c->nlev) return xsb_fail(c, XSB_ERR_ARG, "bad MG level %d", lc);
+  const Level &F = c->lev[lc + 1], &C = c->lev[lc];
+  const int64_t nf = (int64_t)F.A.nb * F.A.bs, nc = (int64_t)C.A.nb * C.A.bs;
+  double *dc = nullptr, *df = nullptr;
+  CUDA_OK(cudaMalloc(&dc, sizeof(double) * nc)); CUDA_OK(cudaMalloc(&df, sizeof(double) * nf));
+  CUDA_OK(cudaMemcpyAsync(df, rf, sizeof(double) * nf, cudaMemcpyHostToDevice, c->stream));
+  int rc = mg_restrict(c, F, C, df, dc);
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(bc, dc, sizeof(double) * nc, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = xsb_fail(c, XSB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  cudaFree(dc); cudaFree(df);
+  return rc;
+}
+int xsb_mg_interpolate_add(xsb_ctx c, int lc, const double *xc, double *xf)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready || lc < 0 || lc + 1 >= c->nlev) return xsb_fail(c, XSB_ERR_ARG, "bad MG level %d", lc);
+  const Level &F = c->lev[lc + 1], &C = c->lev[lc];
+  const int64_t nf = (int64_t)F.A.nb * F.A.bs, nc = (int64_t)C.A.nb * C.A.bs;
+  double *dc = nullptr, *df = nullptr;
+  CUDA_OK(cudaMalloc(&dc, sizeof(double) * nc)); CUDA_OK(cudaMalloc(&df, sizeof(double) * nf));
+  CUDA_OK(cudaMemcpyAsync(dc, xc, sizeof(double) * nc, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(df, xf, sizeof(double) * nf, cudaMemcpyHostToDevice, c->stream));
+  int rc = mg_prolong_add(c, F, C, dc, df);
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(xf, df, sizeof(double) * nf, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = xsb_fail(c, XSB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  cudaFree(dc); cudaFree(df);
+  return rc;
+}
+
+int xsb_ksp_get_iterations(xsb_ctx c, int *its, int *reason) { if (!c) return XSB_ERR_ARG; if (its) *its = c->its; if (reason) *reason = c->reason; return XSB_OK; }
+int xsb_ksp_get_history(xsb_ctx c, double *hist, int cap, int *n)
+{
+  if (!c) return XSB_ERR_ARG;
+  int m = (int)c->hist.size(); if (n) *n = m;
+  for (int i = 0; i < m && i < cap; ++i) hist[i] = c->hist[i];
+  return XSB_OK;
+}
+int xsb_ksp_get_inner_iterations(xsb_ctx c, int *its, int cap, int *n)
+{
+  if (!c) return XSB_ERR_ARG;
+  int m = (int)c->inner_its.size(); if (n) *n = m;
+  for (int i = 0; i < m && i < cap; ++i) its[i] = c->inner_its[i];
+  return XSB_OK;
+}
+int xsb_ksp_get_chebyshev(xsb_ctx c, int level, double *emin_est, double *emax_est, double *emin, double *emax)
+{
+  if (!c || level < 0 || level >= c->nlev) return XSB_ERR_ARG;
+  const Level &L = c->lev[level];
+  if (emin_est) *emin_est = L.emin_est; if (emax_est) *emax_est = L.emax_est; if (emin) *emin = L.emin; if (emax) *emax = L.emax;
+  return XSB_OK;
+}
+int xsb_ksp_get_timing(xsb_ctx c, double *setup_ms, double *solve_ms) { if (!c) return XSB_ERR_ARG; if (setup_ms) *setup_ms = c->setup_ms; if (solve_ms) *solve_ms = c->solve_ms; return XSB_OK; }
+int xsb_ksp_get_counters(xsb_ctx c, int64_t out[8])
+{
+  if (!c || !out) return XSB_ERR_ARG;
+  out[0] = c->n_a00; out[1] = c->n_a; out[2] = c->solve_launches; out[3] = c->a00_timed ? (int64_t)(c->a00_ns_sum / c->a00_timed) : 0;
+  for (int i = 0; i < 4; ++i) out[4 + i] = c->a00_mode[i];
+  return XSB_OK;
+}
+int xsb_get_stream(xsb_ctx c, void **stream) { if (!c || !stream) return XSB_ERR_ARG; *stream = (void *)c->stream; return XSB_OK; }
+
+int xsb_diagnostics(xsb_ctx c, const double *x, double *out)
+{
+  NEED_DEVICE(c);
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_diagnostics before xsb_assemble");
+  const int64_t n = c->lat.n; const int no = 5 * c->nsd + 5;
+  double *dx = nullptr, *dout = nullptr;
+  CUDA_OK(cudaMalloc(&dx, sizeof(double) * n)); CUDA_OK(cudaMalloc(&dout, sizeof(double) * no));
+  CUDA_OK(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  int rc = vec_diagnostics(c, dx, dout);
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(out, dout, sizeof(double) * no, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = xsb_fail(c, XSB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  cudaFree(dx); cudaFree(dout);
+  return rc;
+}
+
+// ---------------------------------------------------------------- host-side index maps (integer logic only)
+static void make_lattice(int nsd, int mx, int my, int mz, Lattice &L)
+{
+  memset(&L, 0, sizeof(L));
+  L.nsd = nsd; L.mx = mx; L.my = my; L.mz = nsd == 3 ? mz : 1;
+  L.NX = 2 * mx + 1; L.NY = 2 * my + 1; L.NZ = nsd == 3 ? 2 * mz + 1 : 1;
+  L.PX = mx + 1; L.PY = my + 1; L.PZ = nsd == 3 ? mz + 1 : 1;
+  L.nun = (int64_t)L.NX * L.NY * L.NZ; L.npn = (int64_t)L.PX * L.PY * L.PZ;
+  L.nu = nsd * L.nun; L.np = L.npn; L.n = L.nu + L.np; L.nel = (int64_t)L.mx * L.my * L.mz;
+}
+
+int xsb_pattern_row(int nsd, int mx, int my, int mz, int64_t row, int32_t *cols, int cap)
+{
+  if ((nsd != 2 && nsd != 3) || mx < 1 || my < 1 || (nsd == 3 && mz < 1)) return XSB_ERR_ARG;
+  Lattice L; make_lattice(nsd, mx, my, mz, L);
+  if (row < 0 || row >= L.n) return XSB_ERR_ARG;
+  RowBox b; int comp; row_to_box(L, row, b, &comp);
+  const int len = nsd * b.ncu + b.ncp;
+  if (!cols) return len;
+  int c = 0;
+  for (int kk = b.ulo[2]; kk <= b.uhi[2]; ++kk) for (int jj = b.ulo[1]; jj <= b.uhi[1]; ++jj) for (int ii = b.ulo[0]; ii <= b.uhi[0]; ++ii)
+    for (int d = 0; d < nsd; ++d) { if (c < cap) cols[c] = (int32_t)(nsd * (ii + (int64_t)jj * L.NX + (int64_t)kk * L.NX * L.NY) + d); c++; }
+  for (int kk = b.plo[2]; kk <= b.phi[2]; ++kk) for (int jj = b.plo[1]; jj <= b.phi[1]; ++jj) for (int ii = b.plo[0]; ii <= b.phi[0]; ++ii)
+  { if (c < cap) cols[c] = (int32_t)(L.nu + ii + (int64_t)jj * L.PX + (int64_t)kk * L.PX * L.PY); c++; }
+  return len;
+}
+
+int64_t xsb_prealloc_total(int nsd, int mx, int my, int mz)
+{
+  Lattice L; make_lattice(nsd, mx, my, mz, L);
+  int64_t tot = 0; const int64_t m = L.n;
+  for (int k = 0; k < L.NZ; ++k) for (int j = 0; j < L.NY; ++j) for (int i = 0; i < L.NX; ++i) {
+    int64_t r;
+    if (nsd == 2) { bool vi = i % 2 == 0, vj = j % 2 == 0; r = (vi && vj) ? 2 * 25 + 9 : (vi || vj) ? 2 * 15 + 6 : 2 * 9 + 4; }   // femixedspace.c:205-211
+    else { int nmod = i % 2 + j % 2 + k % 2; r = nmod == 0 ? 3 * 125 + 27 : nmod == 1 ? 3 * 75 + 18 : nmod == 2 ? 3 * 45 + 12 : 3 * 27 + 8; }   // :231-244
+    if (r > m) r = m;
+    tot += nsd * r;
+  }
+  int64_t r = nsd == 2 ? 2 * 25 + 9 : 3 * 125 + 27; if (r > m) r = m;   // :263, :278
+  return tot + L.npn * r;
+}
+
+int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int mz, int32_t *idx, double *val, int cap)
+{
+  Lattice L; make_lattice(nsd, mx, my, mz, L);
+  const int ni = L.NX, nj = L.NY, nk = L.NZ, N = L.NY, M = L.NX;
+  int type = BC_SOLCX;
+  if (model < 0) model = lame ? 6 : 2;
+  if (lame && model == 8) type = BC_FIXEDBASE;
+  if (lame && (model == 9 || model == 10)) type = BC_COMPRESSION;
+  if (nsd == 3 && model == 11) type = BC_FIXEDBASE;
+  if (lame && nsd == 3 && model == 12) type = BC_COMPRESSION2;
+  if (!lame && nsd == 2 && model == 101) type = BC_MMS1;
+  int cnt = 0;
+  auto push = [&](int i, int j, int k, int d, double v) { if (idx && cnt < cap) { idx[cnt] = nsd * (i + j * ni + k * ni * nj) + d; if (val) val[cnt] = v; } cnt++; };
+  switch (type) {
+  case BC_SOLCX:   // models.c:52-79 (2-D), :98-149 (3-D)
+    if (nsd == 2) {
+      for (int j = 0; j < nj; ++j) push(0, j, 0, 0, 0.0);
+      for (int i = 0; i < ni; ++i) push(i, 0, 0, 1, 0.0);
+      for (int j = 0; j < nj; ++j) push(ni - 1, j, 0, 0, 0.0);
+      if (freeslip) for (int i = 0; i < ni; ++i) push(i, nj - 1, 0, 1, 0.0);
+    } else {
+      for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(0, j, k, 0, 0.0);
+      for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, 0, k, 1, 0.0);
+      for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, 0, 2, 0.0);
+      for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(ni - 1, j, k, 0, 0.0);
+      if (freeslip) for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, nj - 1, k, 1, 0.0);
+      for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, nk - 1, 2, 0.0);
+    }
+    break;
+  case BC_FIXEDBASE:   // models.c:197-225
+    for (int d = 0; d < nsd; ++d) for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, 0, k, d, 0.0);
+    break;
+  case BC_COMPRESSION:   // models.c:276-328 (the x-max test compares with the y count, :270,:288,:315)
+    for (int d = 0; d < nsd; ++d) for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(0, j, k, d, d == 0 ? 0.1 : 0.0);
+    if (ni == N) for (int d = 0; d < nsd; ++d) for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(ni - 1, j, k, d, d == 0 ? -0.1 : 0.0);
+    break;
+  case BC_COMPRESSION2:   // models.c:380-446
+    for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(0, j, k, 0, 0.1);
+    if (ni == N) for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(ni - 1, j, k, 0, -0.1);
+    for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, 0, k, 1, 0.0);
+    for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, 0, 2, 0.0);
+    for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, nk - 1, 2, 0.0);
+    break;
+  case BC_MMS1:   // models.c:505-593; values are filled from the coordinates by the caller
+    for (int j = 0; j < nj; ++j) for (int d = 0; d < 2; ++d) push(0, j, 0, d, 0.0);
+    if (ni == N) for (int j = 0; j < nj; ++j) for (int d = 0; d < 2; ++d) push(ni - 1, j, 0, d, 0.0);
+    for (int i = 0; i < ni; ++i) for (int d = 0; d < 2; ++d) push(i, 0, 0, d, 0.0);
+    if (nj == M) for (int i = 0; i < ni; ++i) for (int d = 0; d < 2; ++d) push(i, nj - 1, 0, d, 0.0);
+    break;
+  }
+  return cnt;
+}
+
+int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, int dims[3])
+{
+  if (levels < 1 || level < 0 || level >= levels) return XSB_ERR_ARG;
+  int n[3] = {2 * mx + 1, 2 * my + 1, nsd == 3 ? 2 * mz + 1 : 1};
+  for (int l = levels - 1; l > level; --l)
+    for (int d = 0; d < 3; ++d) {
+      if (n[d] == 1 && d == 2 && nsd == 2) continue;
+      if ((n[d] - 1) % 2 != 0) return XSB_ERR_ARG;
+      n[d] = (n[d] - 1) / 2 + 1;
+      if (n[d] < 2) return XSB_ERR_ARG;
+    }
+  dims[0] = n[0]; dims[1] = n[1]; dims[2] = n[2];
+  return XSB_OK;
+}
+
+int xsb_slab_range(int mz, int nranks, int rank, int *k0, int *k1)
+{
+  if (nranks < 1 || rank < 0 || rank >= nranks || mz < nranks) return XSB_ERR_ARG;
+  const int q = mz / nranks, r = mz % nranks;
+  const int s = rank * q + (rank < r ? rank : r);
+  if (k0) *k0 = s; if (k1) *k1 = s + q + (rank < r ? 1 : 0);
+  return XSB_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,405 @@
+// xsb_mg.cu -- geometric multigrid on the velocity block (K8, K9, K11 of SURVEY 2.1).
+//
+// Replaces what PETSc's PCMG does for -saddle_fieldsplit_u_pc_type mg with a DMDA (abf.opts:4-13,
+// exSaddle.c:408-422): DMCoarsen ((n-1)/2+1 nodes per direction), DMCreateInterpolation (Q1 on the node
+// lattice, MAIJ over the NSD components), Galerkin P^T A P (MatPtAP), Chebyshev/Jacobi smoothers with the
+// GMRES eigenvalue estimate, LU on the coarsest level.
+//   * transfers are stencil kernels on the lattice (no stored P);
+//   * every level operator is a BAIJ(NSD) "box pattern" matrix, so block positions are closed-form;
+//   * the Galerkin product is a gather: one thread per coarse block, no atomics, fixed summation order;
+//   * the coarsest operator is inverted densely on the device (Gauss-Jordan, SPD => no pivoting) and applied
+//     as a GEMV: the V-cycle has no host round trip at all.
+#include "xsb.h"
+#include <cub/cub.cuh>
+
+static inline unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+// ------------------------------------------------------------------ K8: transfers
+// bc = P^T rf : one thread per coarse node, fine contributions gathered in ascending fine index (MatRestrict)
+template <int BS>
+__global__ void k_restrict(int fnx, int fny, int fnz, int cnx, int cny, int cnz, const double *__restrict__ rf, double *__restrict__ bc)
+{
+  int64_t cn = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (cn >= (int64_t)cnx * cny * cnz) return;
+  const int I = (int)(cn % cnx), J = (int)((cn / cnx) % cny), K = (int)(cn / ((int64_t)cnx * cny));
+  double acc[BS];
+#pragma unroll
+  for (int d = 0; d < BS; ++d) acc[d] = 0.0;
+  for (int c = -1; c <= 1; ++c) for (int b = -1; b <= 1; ++b) for (int a = -1; a <= 1; ++a) {
+    const int i = 2 * I + a, j = 2 * J + b, k = 2 * K + c;
+    if (i < 0 || i >= fnx || j < 0 || j >= fny || k < 0 || k >= fnz) continue;
+    const double w = (a ? 0.5 : 1.0) * (b ? 0.5 : 1.0) * (c ? 0.5 : 1.0);
+    const int64_t f = i + (int64_t)j * fnx + (int64_t)k * fnx * fny;
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[d] += w * rf[BS * f + d];
+  }
+#pragma unroll
+  for (int d = 0; d < BS; ++d) bc[BS * cn + d] = acc[d];
+}
+// xf += P xc : one thread per fine node (MatInterpolateAdd)
+template <int BS>
+__global__ void k_prolong_add(int fnx, int fny, int fnz, int cnx, int cny, const double *__restrict__ xc, double *__restrict__ xf)
+{
+  int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (f >= (int64_t)fnx * fny * fnz) return;
+  const int i = (int)(f % fnx), j = (int)((f / fnx) % fny), k = (int)(f / ((int64_t)fnx * fny));
+  const int i0 = i >> 1, j0 = j >> 1, k0 = k >> 1, ni = 1 + (i & 1), nj = 1 + (j & 1), nk = 1 + (k & 1);
+  const double w = (ni == 2 ? 0.5 : 1.0) * (nj == 2 ? 0.5 : 1.0) * (nk == 2 ? 0.5 : 1.0);
+  double acc[BS];
+#pragma unroll
+  for (int d = 0; d < BS; ++d) acc[d] = 0.0;
+  for (int c = 0; c < nk; ++c) for (int b = 0; b < nj; ++b) for (int a = 0; a < ni; ++a) {
+    const int64_t cn = (i0 + a) + (int64_t)(j0 + b) * cnx + (int64_t)(k0 + c) * cnx * cny;
+#pragma unroll
+    for (int d = 0; d < BS; ++d) acc[d] += w * xc[BS * cn + d];
+  }
+#pragma unroll
+  for (int d = 0; d < BS; ++d) xf[BS * f + d] += acc[d];
+}
+int mg_restrict(xsb_ctx c, const Level &F, const Level &C, const double *rf, double *bc)
+{
+  const int64_t nc = (int64_t)C.nx * C.ny * C.nz;
+  if (c->nsd == 3) k_restrict<3><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, C.nz, rf, bc);
+  else k_restrict<2><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, C.nz, rf, bc);
+  KERNEL_OK(); return 0;
+}
+int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, double *xf)
+{
+  const int64_t nf = (int64_t)F.nx * F.ny * F.nz;
+  if (c->nsd == 3) k_prolong_add<3><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, xc, xf);
+  else k_prolong_add<2><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, xc, xf);
+  KERNEL_OK(); return 0;
+}
+
+// ------------------------------------------------------------------ K9: Galerkin coarse operator
+__global__ void k_box_len(BoxPattern p, int64_t *len)
+{
+  int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (nd >= (int64_t)p.nx * p.ny * p.nz) return;
+  len[nd] = box_size(p, (int)(nd % p.nx), (int)((nd / p.nx) % p.ny), (int)(nd / ((int64_t)p.nx * p.ny)));
+}
+__global__ void k_narrow(int64_t n, const int64_t *a, int *b) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i <= n) b[i] = (int)a[i]; }
+
+// A_c[I,J] = sum_{f in N(I)} sum_{g in N(J), g in box(f)} w(f,I) w(g,J) A[f,g];  one thread per (I, J) coarse block
+template <int BS>
+__global__ void __launch_bounds__(128) k_galerkin(BoxPattern fp, const int *__restrict__ fia, const double *__restrict__ fa,
+                                                  BoxPattern cp, const int *__restrict__ cia, int *__restrict__ cja, double *__restrict__ ca)
+{
+  constexpr int BS2 = BS * BS;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, ncn = (int64_t)cp.nx * cp.ny * cp.nz;
+  const int64_t I = t / 27; const int s27 = (int)(t - I * 27);
+  if (I >= ncn) return;
+  const int Ii = (int)(I % cp.nx), Ij = (int)((I / cp.nx) % cp.ny), Ik = (int)(I / ((int64_t)cp.nx * cp.ny));
+  const int Ji = Ii + s27 % 3 - 1, Jj = Ij + (s27 / 3) % 3 - 1, Jk = Ik + s27 / 9 - 1;
+  if (Ji < 0 || Ji >= cp.nx || Jj < 0 || Jj >= cp.ny || Jk < 0 || Jk >= cp.nz) return;
+  const int slot = box_slot(cp, Ii, Ij, Ik, Ji, Jj, Jk);
+  double acc[BS2];
+#pragma unroll
+  for (int x = 0; x < BS2; ++x) acc[x] = 0.0;
+  for (int fk = 2 * Ik - 1; fk <= 2 * Ik + 1; ++fk) {
+    if (fk < 0 || fk >= fp.nz) continue;
+    for (int fj = 2 * Ij - 1; fj <= 2 * Ij + 1; ++fj) {
+      if (fj < 0 || fj >= fp.ny) continue;
+      for (int fi = 2 * Ii - 1; fi <= 2 * Ii + 1; ++fi) {
+        if (fi < 0 || fi >= fp.nx) continue;
+        const double wf = (fi == 2 * Ii ? 1.0 : 0.5) * (fj == 2 * Ij ? 1.0 : 0.5) * (fk == 2 * Ik ? 1.0 : 0.5);
+        int l0, h0, l1, h1, l2, h2;
+        box_range(fp, fi, fp.nx, l0, h0); box_range(fp, fj, fp.ny, l1, h1); box_range(fp, fk, fp.nz, l2, h2);
+        const int nx = h0 - l0 + 1, ny = h1 - l1 + 1;
+        const int64_t f = fi + (int64_t)fj * fp.nx + (int64_t)fk * fp.nx * fp.ny;
+        const double *rowv = fa + (int64_t)fia[f] * BS2;
+        const int g0 = max(2 * Ji - 1, l0), g1 = min(2 * Ji + 1, h0), gj0 = max(2 * Jj - 1, l1), gj1 = min(2 * Jj + 1, h1), gk0 = max(2 * Jk - 1, l2), gk1 = min(2 * Jk + 1, h2);
+        for (int gk = gk0; gk <= gk1; ++gk) for (int gj = gj0; gj <= gj1; ++gj) for (int gi = g0; gi <= g1; ++gi) {
+          const double w = wf * ((gi == 2 * Ji ? 1.0 : 0.5) * (gj == 2 * Jj ? 1.0 : 0.5) * (gk == 2 * Jk ? 1.0 : 0.5));
+          const double *blk = rowv + (int64_t)(((gk - l2) * ny + (gj - l1)) * nx + (gi - l0)) * BS2;
+#pragma unroll
+          for (int x = 0; x < BS2; ++x) acc[x] += w * blk[x];
+        }
+      }
+    }
+  }
+  const int64_t pos = cia[I] + slot;
+  cja[pos] = (int)(Ji + (int64_t)Jj * cp.nx + (int64_t)Jk * cp.nx * cp.ny);
+#pragma unroll
+  for (int x = 0; x < BS2; ++x) ca[pos * BS2 + x] = acc[x];
+}
+
+static int galerkin(xsb_ctx c, const Level &F, Level &C)
+{
+  const int bs = c->nsd; cudaStream_t st = c->stream;
+  BoxPattern cp{C.nx, C.ny, C.nz, 0};
+  const int64_t ncn = (int64_t)C.nx * C.ny * C.nz;
+  int64_t *len = nullptr; CUDA_OK(cudaMalloc(&len, sizeof(int64_t) * (ncn + 1)));
+  k_box_len<<<nblk(ncn), 256, 0, st>>>(cp, len); KERNEL_OK();
+  CUDA_OK(cudaMemsetAsync(len + ncn, 0, sizeof(int64_t), st));
+  void *tmp = nullptr; size_t tb = 0;
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, len, ncn + 1, st));
+  CUDA_OK(cudaMalloc(&tmp, tb));
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, len, len, ncn + 1, st));
+  int64_t tot = 0; CUDA_OK(cudaMemcpyAsync(&tot, len + ncn, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(tmp));
+  Baij &A = C.A; A.nb = (int)ncn; A.bs = bs; A.nblk = tot; A.pat = cp;
+  XSB_CHK(dev_alloc(c, &A.ia, (size_t)ncn + 1)); XSB_CHK(dev_alloc(c, &A.ja, (size_t)tot)); XSB_CHK(dev_alloc(c, &A.a, (size_t)tot * bs * bs));
+  k_narrow<<<nblk(ncn + 1), 256, 0, st>>>(ncn, len, A.ia); KERNEL_OK();
+  if (bs == 3) k_galerkin<3><<<nblk(ncn * 27, 128), 128, 0, st>>>(F.A.pat, F.A.ia, F.A.a, cp, A.ia, A.ja, A.a);
+  else k_galerkin<2><<<nblk(ncn * 27, 128), 128, 0, st>>>(F.A.pat, F.A.ia, F.A.a, cp, A.ia, A.ja, A.a);
+  KERNEL_OK();
+  CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(len));
+  C.owns_A = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------ Jacobi (PCSetUp_Jacobi: 1/diag, zero -> 1)
+template <int BS>
+__global__ void k_baij_idiag(BoxPattern p, const int *__restrict__ ia, const double *__restrict__ a, double *__restrict__ idiag)
+{
+  int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (nd >= (int64_t)p.nx * p.ny * p.nz) return;
+  const int i = (int)(nd % p.nx), j = (int)((nd / p.nx) % p.ny), k = (int)(nd / ((int64_t)p.nx * p.ny));
+  const int slot = box_slot(p, i, j, k, i, j, k);
+  const double *blk = a + (int64_t)(ia[nd] + slot) * BS * BS;
+  for (int d = 0; d < BS; ++d) { double v = blk[d * BS + d]; idiag[BS * nd + d] = v == 0.0 ? 1.0 : 1.0 / v; }
+}
+int baij_diag_inv(xsb_ctx c, const Baij &A, double *idiag)
+{
+  if (A.bs == 3) k_baij_idiag<3><<<nblk(A.nb), 256, 0, c->stream>>>(A.pat, A.ia, A.a, idiag);
+  else k_baij_idiag<2><<<nblk(A.nb), 256, 0, c->stream>>>(A.pat, A.ia, A.a, idiag);
+  KERNEL_OK(); return 0;
+}
+__global__ void k_csr_idiag(int n, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, double *__restrict__ idiag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  double v = 0.0; for (int k = ia[i]; k < ia[i + 1]; ++k) if (ja[k] == i) v = a[k];
+  idiag[i] = v == 0.0 ? 1.0 : 1.0 / v;
+}
+int csr_diag_inv(xsb_ctx c, const Csr &A, double *idiag) { k_csr_idiag<<<nblk(A.n), 256, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, idiag); KERNEL_OK(); return 0; }
+
+// BAIJ -> scalar CSR on the host (MatGetRowIJ view of a level operator; used by tests / xsb_mat_get_csr)
+int baij_to_csr_host(xsb_ctx c, const Baij &A, int32_t *ia, int32_t *ja, double *a)
+{
+  const int bs = A.bs, bs2 = bs * bs;
+  std::vector<int> bia(A.nb + 1), bja(A.nblk); std::vector<double> ba;
+  CUDA_OK(cudaMemcpy(bia.data(), A.ia, sizeof(int) * (A.nb + 1), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(bja.data(), A.ja, sizeof(int) * A.nblk, cudaMemcpyDeviceToHost));
+  if (a) { ba.resize((size_t)A.nblk * bs2); CUDA_OK(cudaMemcpy(ba.data(), A.a, sizeof(double) * A.nblk * bs2, cudaMemcpyDeviceToHost)); }
+  int64_t pos = 0;
+  for (int nd = 0; nd < A.nb; ++nd) {
+    const int nb = bia[nd + 1] - bia[nd];
+    for (int x = 0; x < bs; ++x) {
+      if (ia) ia[bs * nd + x] = (int32_t)pos;
+      for (int s = 0; s < nb; ++s) for (int y = 0; y < bs; ++y) {
+        if (ja) ja[pos] = bs * bja[bia[nd] + s] + y;
+        if (a) a[pos] = ba[(size_t)(bia[nd] + s) * bs2 + x * bs + y];
+        pos++;
+      }
+    }
+  }
+  if (ia) ia[bs * A.nb] = (int32_t)pos;
+  return 0;
+}
+
+// ------------------------------------------------------------------ K11: dense inverse of the coarsest operator
+template <int BS>
+__global__ void k_baij_to_dense(int nb, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, int n, double *__restrict__ M)
+{
+  int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per block row (coarsest level is tiny)
+  if (blk >= nb) return;
+  for (int s = ia[blk]; s < ia[blk + 1]; ++s) for (int x = 0; x < BS; ++x) for (int y = 0; y < BS; ++y)
+    M[(int64_t)(BS * blk + x) * n + BS * ja[s] + y] = a[(int64_t)s * BS * BS + x * BS + y];
+}
+__global__ void k_gj_prepare(int n, int k, const double *__restrict__ M, double *__restrict__ colk, double *__restrict__ rowk, int *__restrict__ flag)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x; if (t >= n) return;
+  const double piv = M[(int64_t)k * n + k];
+  if (t == 0 && piv == 0.0) *flag = 1;
+  const double p = 1.0 / piv;
+  colk[t] = M[(int64_t)t * n + k];
+  rowk[t] = t == k ? p : M[(int64_t)k * n + t] * p;
+}
+__global__ void k_gj_update(int n, int k, double *__restrict__ M, const double *__restrict__ colk, const double *__restrict__ rowk)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n) return;
+  double *m = M + (int64_t)i * n + j;
+  if (i == k) *m = rowk[j];
+  else if (j == k) *m = -colk[i] * rowk[k];
+  else *m = *m - colk[i] * rowk[j];
+}
+__global__ void k_gemv(int n, const double *__restrict__ M, const double *__restrict__ b, double *__restrict__ x)
+{
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double acc = 0.0;
+  for (int j = lane; j < n; j += 32) acc += M[(int64_t)row * n + j] * b[j];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) x[row] = acc;
+}
+static int coarse_invert(xsb_ctx c, Level &L)
+{
+  const int n = L.A.nb * L.A.bs; cudaStream_t st = c->stream;
+  if (n > 6600) return xsb_fail(c, XSB_ERR_SUP, "coarsest MG level has %d dofs; the dense coarse solve supports <= 6600 (use more -saddle_fieldsplit_u_pc_mg_levels)", n);
+  XSB_CHK(dev_alloc(c, &L.inv, (size_t)n * n));
+  CUDA_OK(cudaMemsetAsync(L.inv, 0, sizeof(double) * n * n, st));
+  if (L.A.bs == 3) k_baij_to_dense<3><<<nblk(L.A.nb, 64), 64, 0, st>>>(L.A.nb, L.A.ia, L.A.ja, L.A.a, n, L.inv);
+  else k_baij_to_dense<2><<<nblk(L.A.nb, 64), 64, 0, st>>>(L.A.nb, L.A.ia, L.A.ja, L.A.a, n, L.inv);
+  KERNEL_OK();
+  double *colk = nullptr, *rowk = nullptr; int *flag = nullptr;
+  XSB_CHK(dev_alloc(c, &colk, (size_t)n)); XSB_CHK(dev_alloc(c, &rowk, (size_t)n)); XSB_CHK(dev_alloc(c, &flag, 1));
+  CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  dim3 g2((n + 255) / 256, n);
+  for (int k = 0; k < n; ++k) {
+    k_gj_prepare<<<nblk(n), 256, 0, st>>>(n, k, L.inv, colk, rowk, flag); KERNEL_OK();
+    k_gj_update<<<g2, 256, 0, st>>>(n, k, L.inv, colk, rowk); KERNEL_OK();
+  }
+  int hflag = 0; CUDA_OK(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  if (hflag) return xsb_fail(c, XSB_ERR_BREAKDOWN, "zero pivot in the coarse-level factorisation");
+  return 0;
+}
+
+// ------------------------------------------------------------------ Chebyshev / Jacobi smoother (App. B.4)
+__global__ void k_cheb_first_zero(int64_t n, double scale, const double *__restrict__ idiag, const double *__restrict__ b, double *__restrict__ p)
+{ for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.0 + scale * (idiag[i] * b[i]); }
+
+static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, double *y, const Epilogue &ep)
+{
+  return fine ? spmv_a00_fine(c, L.A, x, y, ep) : spmv_baij(c, L.A, x, y, ep);
+}
+
+// KSPSolve_Chebyshev, Jacobi PC, nonzero initial guess, norm none: first correction + (its-1) recurrence steps.
+// Result ends in L.x (buffers are rotated by pointer swap, no copies).
+static int cheb_smooth(xsb_ctx c, Level &L, bool fine, int its, bool x_is_zero)
+{
+  if (its < 1) return 0;
+  const int64_t n = (int64_t)L.A.nb * L.A.bs;
+  const double scale = 2.0 / (L.emax + L.emin), alpha = 1.0 - scale * L.emin, mu = 1.0 / alpha, omegaprod = 2.0 / alpha;
+  double ckm1 = 1.0, ck = mu;
+  double *pkm1 = L.x, *pk = L.w0, *pkp1 = L.w1;
+  if (x_is_zero) {   // r = b - A*0 = b exactly: skip the product (bitwise identical)
+    k_cheb_first_zero<<<nblk(n) > 2368 ? 2368 : nblk(n), 256, 0, c->stream>>>(n, scale, L.idiag, L.b, pk); KERNEL_OK();
+  } else {
+    Epilogue ep; ep.mode = EPI_CHEB_FIRST; ep.b = L.b; ep.idiag = L.idiag; ep.pk = pkm1; ep.s0 = scale;
+    XSB_CHK(a00_spmv(c, L, fine, pkm1, pk, ep));
+  }
+  for (int it = 1; it < its; ++it) {
+    const double ckp1 = 2.0 * mu * ck - ckm1, omega = omegaprod * ck / ckp1;
+    Epilogue ep; ep.mode = EPI_CHEB; ep.b = L.b; ep.idiag = L.idiag; ep.pk = pk; ep.pkm1 = pkm1;
+    ep.s0 = 1.0 - omega; ep.s1 = omega; ep.s2 = omega * scale;
+    XSB_CHK(a00_spmv(c, L, fine, pk, pkp1, ep));
+    ckm1 = ck; ck = ckp1;
+    double *t = pkm1; pkm1 = pk; pk = pkp1; pkp1 = t;
+  }
+  L.x = pk; L.w0 = pkm1; L.w1 = pkp1;
+  return 0;
+}
+
+static int mg_cycle(xsb_ctx c, int l)
+{
+  Level &L = c->lev[l];
+  if (l == 0) {   // coarse grid: preonly + LU  ->  x = A^-1 b
+    const int n = L.A.nb * L.A.bs;
+    k_gemv<<<nblk((int64_t)n * 32), 256, 0, c->stream>>>(n, L.inv, L.b, L.x); KERNEL_OK();
+    return 0;
+  }
+  Level &C = c->lev[l - 1];
+  const bool fine = l == c->nlev - 1;
+  const int64_t n = (int64_t)L.A.nb * L.A.bs;
+  XSB_CHK(vec_set(c, n, 0.0, L.x));
+  XSB_CHK(cheb_smooth(c, L, fine, c->so.cheb_its, true));                 // pre-smooth
+  { Epilogue ep; ep.mode = EPI_RESIDUAL; ep.b = L.b; XSB_CHK(a00_spmv(c, L, fine, L.x, L.r, ep)); }   // r = b - A x
+  XSB_CHK(mg_restrict(c, L, C, L.r, C.b));
+  XSB_CHK(mg_cycle(c, l - 1));
+  XSB_CHK(mg_prolong_add(c, L, C, C.x, L.x));
+  XSB_CHK(cheb_smooth(c, L, fine, c->so.cheb_its, false));                // post-smooth
+  return 0;
+}
+
+// PCApply_MG: one multiplicative V-cycle from a zero initial guess
+int mg_vcycle(xsb_ctx c, const double *b, double *x)
+{
+  Level &L = c->lev[c->nlev - 1];
+  const int64_t n = (int64_t)L.A.nb * L.A.bs;
+  double *save = L.b; L.b = const_cast<double *>(b);   // the level reads b in place
+  int rc = mg_cycle(c, c->nlev - 1);
+  L.b = save;
+  if (rc) return rc;
+  return vec_copy(c, n, L.x, x);
+}
+
+// ------------------------------------------------------------------ eigenvalue estimate (KSPChebyshev esteig)
+// eststeps of left-Jacobi GMRES (classical Gram-Schmidt) on the noisy vector; Ritz values of the Hessenberg.
+static int cheb_estimate(xsb_ctx c, Level &L)
+{
+  const SolverOpts &s = c->so; const int m = s.esteig_steps; const int64_t n = (int64_t)L.A.nb * L.A.bs;
+  std::vector<double *> V(m + 1, nullptr);
+  for (auto &v : V) XSB_CHK(dev_alloc(c, &v, (size_t)n));
+  double *t = L.r;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), h(m + 2);
+  XSB_CHK(vec_rander48(c, n, s.noise, t));
+  XSB_CHK(vec_pmult(c, n, L.idiag, t, V[0]));                       // v0 = M^-1 b (x0 = 0)
+  XSB_CHK(vec_mdot(c, n, V[0], V.data(), 0, true, c->scal));
+  XSB_CHK(vec_fetch(c, c->scal, 1, h.data()));
+  const double res0 = sqrt(h[0]); double res = res0;
+  if (res0 == 0.0) return xsb_fail(c, XSB_ERR_BREAKDOWN, "zero noise vector in the Chebyshev eigenvalue estimate");
+  XSB_CHK(vec_scale(c, n, 1.0 / res0, V[0]));
+  std::vector<double> cs(m + 1), sn(m + 1), rs(m + 1); rs[0] = res0;
+  int it = 0;
+  while (it < m) {
+    Epilogue ep;
+    XSB_CHK(spmv_baij(c, L.A, V[it], t, ep));
+    XSB_CHK(vec_pmult(c, n, L.idiag, t, V[it + 1]));               // w = M^-1 A v
+    XSB_CHK(vec_mdot(c, n, V[it + 1], V.data(), it + 1, false, c->scal));
+    XSB_CHK(vec_maxpy_dev(c, n, V[it + 1], V.data(), it + 1, c->scal, -1.0));
+    XSB_CHK(vec_mdot(c, n, V[it + 1], V.data(), 0, true, c->scal + it + 1));
+    XSB_CHK(vec_scale_by_inv_sqrt(c, n, V[it + 1], c->scal + it + 1));
+    XSB_CHK(vec_fetch(c, c->scal, it + 2, h.data()));
+    const double tt = sqrt(h[it + 1]);
+    for (int j = 0; j <= it; ++j) H[(size_t)j * m + it] = h[j];
+    H[(size_t)(it + 1) * m + it] = tt;
+    // Givens update only to track the residual for the rtol 1e-12 stop (KSPSetTolerances(kspest,1e-12,...))
+    std::vector<double> col(h.begin(), h.begin() + it + 1); col.push_back(tt);
+    for (int j = 0; j < it; ++j) { double a = col[j]; col[j] = cs[j] * a + sn[j] * col[j + 1]; col[j + 1] = -sn[j] * a + cs[j] * col[j + 1]; }
+    const double d = sqrt(col[it] * col[it] + col[it + 1] * col[it + 1]);
+    it++;
+    if (d == 0.0) break;
+    cs[it - 1] = col[it - 1] / d; sn[it - 1] = col[it] / d;
+    rs[it] = -sn[it - 1] * rs[it - 1]; rs[it - 1] = cs[it - 1] * rs[it - 1];
+    res = fabs(rs[it]);
+    if (res <= 1e-12 * res0 || tt == 0.0) break;
+  }
+  std::vector<double> Hk((size_t)it * it), wr(it), wi(it);
+  for (int i = 0; i < it; ++i) for (int j = 0; j < it; ++j) Hk[(size_t)i * it + j] = H[(size_t)i * m + j];
+  if (hess_eig(it, Hk.data(), it, wr.data(), wi.data())) return xsb_fail(c, XSB_ERR_BREAKDOWN, "Hessenberg eigenvalue iteration failed");
+  L.emin_est = wr[0]; L.emax_est = wr[0];
+  for (int i = 1; i < it; ++i) { if (wr[i] < L.emin_est) L.emin_est = wr[i]; if (wr[i] > L.emax_est) L.emax_est = wr[i]; }
+  L.emin = s.esteig[0] * L.emin_est + s.esteig[1] * L.emax_est;
+  L.emax = s.esteig[2] * L.emin_est + s.esteig[3] * L.emax_est;
+  return 0;
+}
+
+// ------------------------------------------------------------------ PCSetUp_MG
+int mg_setup(xsb_ctx c)
+{
+  const SolverOpts &s = c->so; const int levels = s.mg_levels; const Lattice &Lt = c->lat;
+  if (levels < 1 || levels > XSB_MAX_LEVELS) return xsb_fail(c, XSB_ERR_ARG, "-saddle_fieldsplit_u_pc_mg_levels %d out of range", levels);
+  c->nlev = levels;
+  { Level &L = c->lev[levels - 1]; L = Level(); L.nx = Lt.NX; L.ny = Lt.NY; L.nz = Lt.NZ; L.A = c->A00; L.owns_A = false; }
+  for (int l = levels - 2; l >= 0; --l) {
+    Level &F = c->lev[l + 1], &C = c->lev[l]; C = Level();
+    int dims[3];
+    if (xsb_mg_level_dims(c->nsd, Lt.mx, Lt.my, Lt.mz, levels, l, dims)) return xsb_fail(c, XSB_ERR_ARG, "mesh %dx%dx%d cannot be coarsened to %d MG levels (DMCoarsen needs (n-1) divisible by 2)", Lt.mx, Lt.my, Lt.mz, levels);
+    C.nx = dims[0]; C.ny = dims[1]; C.nz = dims[2];
+    XSB_CHK(galerkin(c, F, C));
+  }
+  for (int l = 0; l < levels; ++l) {
+    Level &L = c->lev[l]; const int64_t n = (int64_t)L.A.nb * L.A.bs;
+    XSB_CHK(dev_alloc(c, &L.x, (size_t)n)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)n));
+    XSB_CHK(dev_alloc(c, &L.w0, (size_t)n)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)n)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
+    XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
+  }
+  XSB_CHK(coarse_invert(c, c->lev[0]));
+  for (int l = 1; l < levels; ++l) {
+    Level &L = c->lev[l];
+    if (s.n_cheb_fixed > 0) {
+      if (l - 1 >= s.n_cheb_fixed) return xsb_fail(c, XSB_ERR_ARG, "explicit Chebyshev eigenvalues missing for MG level %d", l);
+      L.emin = s.cheb_emin[l - 1]; L.emax = s.cheb_emax[l - 1];
+    } else XSB_CHK(cheb_estimate(c, L));
+  }
+  return 0;
+}

@@ -1,0 +1,153 @@
+// xsb_spmv.cu -- operator application kernels (K1/K2/K3 of SURVEY 2.1).
+//
+// Replace PETSc MatMult on the AIJ matrices the reference fills (KSPSolve, exSaddle.c:425; rhs_diri,
+// femixedspace.c:2639).  Both kernels are HBM-bandwidth bound (2 flop per 12 B / 8.4 B of matrix):
+//   spmv_csr   AIJ layout (the reference's MATAIJ): one warp per row, lanes stride the row so every
+//              load instruction of values / column indices is a contiguous 256 B / 128 B segment;
+//              matrix stream uses ld.global.cs (evict-first) so the 126 MB L2 stays available for x.
+//   spmv_baij  BAIJ(bs) velocity block A00 and every Galerkin level: one warp per block row, lanes stride
+//              the row's bs*bs*nblocks doubles flat (coalesced), block column index broadcast from L1,
+//              three per-component accumulators reduced by warp shuffles.  The epilogue fuses the vector
+//              work that always follows the product in the smoother (residual / Chebyshev update), so the
+//              smoother makes exactly one pass over A00 per iteration and no separate vector passes.
+#include "xsb.h"
+
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ K1: CSR
+template <int UNROLL>
+__global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t n, const int *__restrict__ ia, const int *__restrict__ ja,
+                                                       const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    const int k0 = ia[row], k1 = ia[row + 1];
+    double acc = 0.0;
+    int k = k0 + lane;
+    for (; k + 32 * (UNROLL - 1) < k1; k += 32 * UNROLL) {
+      double v[UNROLL]; int cidx[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) { v[u] = ld_stream(a + k + 32 * u); cidx[u] = ld_stream(ja + k + 32 * u); }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) acc += v[u] * __ldg(x + cidx[u]);
+    }
+    for (; k < k1; k += 32) acc += ld_stream(a + k) * __ldg(x + ld_stream(ja + k));
+    acc = warp_sum(acc);
+    if (lane == 0) y[row] = acc;
+  }
+}
+
+int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y)
+{
+  if (A.n == 0) return XSB_OK;
+  const int64_t warps = A.n; const int tpb = 256;
+  int64_t blocks = (warps * 32 + tpb - 1) / tpb;
+  const int64_t cap = 148LL * 8 * 16;   // persistent-style grid: 148 SMs x 8 resident CTAs x 16 waves
+  if (blocks > cap) blocks = cap;
+  spmv_csr_kernel<4><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, x, y); KERNEL_OK();
+  return XSB_OK;
+}
+
+// ------------------------------------------------------------------ K2: BAIJ with fused epilogue
+template <int BS>
+__device__ __forceinline__ void epilogue_store(const Epilogue &ep, int64_t node, int lane, const double (&acc)[3], double *__restrict__ y)
+{
+  // lanes 0..BS-1 each finish one component of the block row
+  if (lane < BS) {
+    const int64_t i = (int64_t)BS * node + lane;
+    const double ax = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
+    double out;
+    switch (ep.mode) {
+    case EPI_RESIDUAL:   out = ep.b[i] - ax; break;                                         // r = b - A x
+    case EPI_CHEB_FIRST: out = ep.pk[i] + ep.s0 * (ep.idiag[i] * (ep.b[i] - ax)); break;    // p1 = x + scale*B(b - A x)
+    case EPI_CHEB:       out = ep.s0 * ep.pkm1[i] + ep.s1 * ep.pk[i] + ep.s2 * (ep.idiag[i] * (ep.b[i] - ax)); break; // VecAXPBYPCZ
+    default:             out = ax;
+    }
+    y[i] = out;
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(256) spmv_baij_kernel(int nb, const int *__restrict__ ia, const int *__restrict__ ja,
+                                                        const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y, Epilogue ep)
+{
+  constexpr int BS2 = BS * BS;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t node = warp; node < nb; node += nwarps) {
+    const int b0 = ia[node], nblk = ia[node + 1] - b0;
+    const int len = nblk * BS2;
+    const double *__restrict__ av = a + (int64_t)b0 * BS2;
+    const int *__restrict__ cj = ja + b0;
+    double acc[3] = {0.0, 0.0, 0.0};
+    // element t of the flat block row: block t/BS2, entry r = t%BS2 = (row comp r/BS, col comp r%BS)
+    int t = lane, blk = lane / BS2, r = lane - blk * BS2;
+    constexpr int DB = 32 / BS2, DR = 32 - DB * BS2;   // t += 32  =>  blk += DB, r += DR (mod BS2)
+    for (; t + 96 < len; t += 128) {
+      double v[4]; int bb[4], rr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = ld_stream(av + t + 32 * u); bb[u] = blk; rr[u] = r;
+        blk += DB; r += DR; if (r >= BS2) { r -= BS2; blk += 1; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ra = rr[u] / BS, ca = rr[u] - ra * BS;
+        const double p = v[u] * __ldg(x + (int64_t)BS * __ldg(cj + bb[u]) + ca);
+        acc[0] += ra == 0 ? p : 0.0; acc[1] += ra == 1 ? p : 0.0; if (BS == 3) acc[2] += ra == 2 ? p : 0.0;
+      }
+    }
+    for (; t < len; t += 32) {
+      const int ra = r / BS, ca = r - ra * BS;
+      const double p = ld_stream(av + t) * __ldg(x + (int64_t)BS * __ldg(cj + blk) + ca);
+      acc[0] += ra == 0 ? p : 0.0; acc[1] += ra == 1 ? p : 0.0; if (BS == 3) acc[2] += ra == 2 ? p : 0.0;
+      blk += DB; r += DR; if (r >= BS2) { r -= BS2; blk += 1; }
+    }
+    acc[0] = warp_sum(acc[0]); acc[1] = warp_sum(acc[1]); if (BS == 3) acc[2] = warp_sum(acc[2]);
+    epilogue_store<BS>(ep, node, lane, acc, y);
+  }
+}
+
+int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep)
+{
+  if (A.nb == 0) return XSB_OK;
+  const int tpb = 256; int64_t blocks = ((int64_t)A.nb * 32 + tpb - 1) / tpb;
+  const int64_t cap = 148LL * 8 * 16;
+  if (blocks > cap) blocks = cap;
+  if (A.bs == 3) spmv_baij_kernel<3><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
+  else if (A.bs == 2) spmv_baij_kernel<2><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
+  else return xsb_fail(c, XSB_ERR_SUP, "BAIJ block size %d", A.bs);
+  KERNEL_OK();
+  return XSB_OK;
+}
+
+// Fine-level A00 launch with bookkeeping: per-mode launch counters (for the algorithmic byte count) and, with
+// -xsb_time_kernels, a CUDA-event pair recorded on the launching stream around the kernel.  Events are only
+// read back after the solve (spmv_collect_timing), so timing adds no synchronisation to the timed region.
+int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep)
+{
+  c->n_a00++; c->a00_mode[ep.mode & 3]++;
+  const bool timed = c->so.time_kernels;
+  if (timed) {
+    if (c->ev_used + 2 > c->evpool.size()) { for (int i = 0; i < 256; ++i) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); c->evpool.push_back(e); } }
+    CUDA_OK(cudaEventRecord(c->evpool[c->ev_used], c->stream));
+  }
+  XSB_CHK(spmv_baij(c, A, x, y, ep));
+  if (timed) { CUDA_OK(cudaEventRecord(c->evpool[c->ev_used + 1], c->stream)); c->ev_used += 2; }
+  return XSB_OK;
+}
+int spmv_collect_timing(xsb_ctx c)
+{
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) { float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, c->evpool[i], c->evpool[i + 1])); c->a00_ns_sum += 1e6 * (double)ms; c->a00_timed++; }
+  c->ev_used = 0;
+  return XSB_OK;
+}

@@ -1,0 +1,65 @@
+"""Drop-in front end: reproduces the stdout of ./exSaddle{2d,3d}{,_lame} <options> (exSaddle.c:105-566)
+for the solver trees this library covers, so the reference's testref/*.ref files can be diffed directly."""
+from .api import ExSaddle
+
+_REASON = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS", -4: "DIVERGED_DTOL", -5: "DIVERGED_BREAKDOWN"}
+
+
+def monitor_short(v):
+    """KSPMonitorDefaultShort number format."""
+    if v > 1.e-9:
+        return "%g" % v
+    if v > 1.e-11:
+        return "%5.3e" % v
+    return "< 1.e-11"
+
+
+def diagnostics_text(nsd, d):
+    """SaddleReportSolutionDiagnostics (exSaddle_io.c:17-56)."""
+    tag = "|u,v|" if nsd == 2 else "|u,v,w|"
+    names = ("_1  ", "_2  ", "_inf", "_min", "_max")
+    lines = []
+    for k, nm in enumerate(names):
+        lines.append("%s%s %s%s" % (tag, nm, " , ".join("%+1.6e" % d[k * nsd + c] for c in range(nsd)), " " if nsd == 2 else ""))
+    for k, nm in enumerate(names):
+        lines.append("|p|%s        %+1.6e" % (nm, d[5 * nsd + k]))
+    return lines
+
+
+def run_exsaddle(exe, options, options_file_dir=None):
+    """exe in {exSaddle2d, exSaddle3d, exSaddle2d_lame, exSaddle3d_lame}; returns (stdout_text, ExSaddle, x)."""
+    import os
+    nsd = 2 if "2d" in exe else 3
+    lame = "lame" in exe
+    s = ExSaddle(nsd=nsd, lame=lame)
+    toks = options.split()
+    if "-options_file" in toks:
+        i = toks.index("-options_file"); path = toks[i + 1]
+        if not os.path.isabs(path) and options_file_dir:
+            path = os.path.join(options_file_dir, path)
+        s.set_options(" ".join(toks[:i] + toks[i + 2:]))
+        s.set_options_file(path)
+    else:
+        s.set_options(options)
+    out = []
+    out.append(s.banner().rstrip("\n"))
+    s.assemble()
+    s.ksp_setup()
+    x = s.solve()
+    its, reason = s.iterations()
+    if "-saddle_ksp_monitor_short" in toks:
+        out.append("  Residual norms for saddle_ solve.")
+        inner = s.inner_iterations()
+        show_inner = "-saddle_fieldsplit_u_ksp_converged_reason" in toks
+        for i, r in enumerate(s.history()):
+            if show_inner and i > 0 and i - 1 < len(inner):
+                out.append("  Linear saddle_fieldsplit_u_ solve converged due to CONVERGED_RTOL iterations %d" % inner[i - 1])
+            out.append("%3d KSP Residual norm %s " % (i, monitor_short(r)))
+    if "-saddle_ksp_converged_reason" in toks:
+        if reason > 0:
+            out.append("Linear saddle_ solve converged due to %s iterations %d" % (_REASON.get(reason, str(reason)), its))
+        else:
+            out.append("Linear saddle_ solve did not converge due to %s iterations %d" % (_REASON.get(reason, str(reason)), its))
+    if "-diagnostics" in toks:
+        out.extend(diagnostics_text(nsd, s.diagnostics(x)))
+    return "\n".join(out) + "\n", s, x

@@ -1,0 +1,257 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs,
+against the reference's golden outputs (tests/golden/testref_kat.json), and -- at sizes where the oracle is
+slow -- through size-independent properties.  Bars (BASELINE.json north_star): sparsity pattern and index maps
+bit-exact; operator apply <= 1e-12 relative; residual histories <= 1e-8 relative with equal iteration counts."""
+import numpy as np
+import pytest
+
+import exsaddle_b200 as X
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ABF = " ".join(l for l in O.ABF_OPTS.split("\n") if l.strip())
+
+CASES = [  # (id, nsd, lame, options)
+    ("stokes2d_solcx", 2, False, "-model 0 -mx 4"),
+    ("stokes2d_noncubic", 2, False, "-model 6 -mx 5 -my 3 -eta1 100"),
+    ("stokes3d_sinkers_noncubic", 3, False, "-model 1 -mx 4 -my 7 -mz 5 -eta1 10"),
+    ("stokes3d_sinker6", 3, False, "-model 6 -mx 6 -eta0 1 -eta1 1e6"),
+    ("stokes3d_pseudoice", 3, False, "-model 11 -size_x 0.1 -mx 6"),
+    ("stokes3d_solcx_aspect", 3, False, "-model 0 -mx 6 -size_z 0.1 -eta1 1e3"),
+    ("lame3d_inclusion", 3, True, "-model 6 -mx 4"),
+    ("lame3d_compression", 3, True, "-model 9 -mx 4"),
+    ("lame3d_compression2", 3, True, "-model 12 -mx 4 -mu1 10 -lambda1 100"),
+    ("lame2d_xsinker", 2, True, "-model 2 -mx 8 -mu1 100 -lambda1 10"),
+    ("stokes2d_mms", 2, False, "-model 101 -mx 6"),
+    ("stokes3d_tiny", 3, False, "-model 2 -mx 1"),
+]
+
+
+def _relerr(a, b):
+    s = max(np.max(np.abs(b)), 1e-300)
+    return np.max(np.abs(a - b)) / s
+
+
+@pytest.fixture(scope="module", params=CASES, ids=[c[0] for c in CASES])
+def pair(request):
+    _, nsd, lame, opts = request.param
+    g = X.ExSaddle(opts, nsd=nsd, lame=lame).assemble()
+    o = O.Problem(opts, nsd=nsd, lame=lame)
+    yield g, o
+    g.close()
+
+
+# ------------------------------------------------------------------ set-up parity
+def test_sizes_and_pattern_bit_exact(pair):
+    g, o = pair
+    assert (g.n, g.nu, g.np_, g.nnz, g.prealloc, g.nel, g.nbc, g.mnnz) == (o.n, o.nu, o.np_, o.nnz, o.prealloc, o.nel, o.nbc, o.mnnz)
+    ia, ja, a, _ = g.mat_csr(X.MAT_A)
+    A = o.A()
+    assert ia.dtype == np.int32 and np.array_equal(ia, A.ia) and np.array_equal(ja, A.ja)
+    mia, mja, ma, _ = g.mat_csr(X.MAT_MP)
+    M = o.Mp()
+    assert np.array_equal(mia, M.ia) and np.array_equal(mja, M.ja)
+    bi, bv = g.bc(); oi, ov = o.bc()
+    assert np.array_equal(bi, oi) and np.allclose(bv, ov, rtol=1e-15, atol=0)
+
+
+def test_assembled_values_rhs_and_coefficients(pair):
+    g, o = pair
+    _, _, a, _ = g.mat_csr(X.MAT_A)
+    assert _relerr(a, o.A().a) <= 1e-13
+    _, _, ma, _ = g.mat_csr(X.MAT_MP)
+    assert _relerr(ma, o.Mp().a) <= 1e-13
+    assert _relerr(g.rhs(), o.F()) <= 1e-13
+    cq = o.coeff_qp()
+    for gs, os_ in ((0, 0), (1, 1), (2, 2), (3, 3), (4, 4), (5, 5)):   # slot order is shared: eta,Fu0,Fu1,Fu2,Fp,lambda
+        assert _relerr(g.coeff_qp(gs), cq[:, :, os_].reshape(-1)) <= 1e-14
+
+
+def test_subblocks_are_index_set_extractions(pair):
+    g, o = pair
+    for which, rb, cb in ((X.MAT_A00, 0, 0), (X.MAT_A01, 0, 1), (X.MAT_A10, 1, 0), (X.MAT_A11, 1, 1)):
+        ia, ja, a, shape = g.mat_csr(which)
+        S = o.submatrix(rb, cb)
+        assert shape == S.shape and np.array_equal(ia, S.ia) and np.array_equal(ja, S.ja)
+        assert _relerr(a, S.a) <= 1e-13 if len(a) and np.max(np.abs(S.a)) > 0 else np.all(a == 0)
+
+
+def test_matmult_within_1e12(pair):
+    g, o = pair
+    rng = np.random.default_rng(7)
+    for x in (np.sin(0.37 * np.arange(o.n)) + 0.1, rng.standard_normal(o.n)):
+        y = g.mat_mult(X.MAT_A, x); yo = o.mult(x)
+        assert np.linalg.norm(y - yo) <= 1e-12 * np.linalg.norm(yo)
+        # blocks reproduce the full operator: A x = [A00 xu + A01 xp ; A10 xu + A11 xp]
+        xu, xp = x[:o.nu], x[o.nu:]
+        yb = np.concatenate([g.mat_mult(X.MAT_A00, xu) + g.mat_mult(X.MAT_A01, xp), g.mat_mult(X.MAT_A10, xu) + g.mat_mult(X.MAT_A11, xp)])
+        assert np.linalg.norm(yb - yo) <= 1e-12 * np.linalg.norm(yo)
+    assert np.array_equal(g.mat_diagonal(X.MAT_A), o.A().scipy().diagonal()) or _relerr(g.mat_diagonal(X.MAT_A), o.A().scipy().diagonal()) <= 1e-13
+
+
+def test_operator_is_symmetric_and_linear(pair):
+    g, o = pair
+    rng = np.random.default_rng(3)
+    x, y = rng.standard_normal(o.n), rng.standard_normal(o.n)
+    Ax, Ay = g.mat_mult(X.MAT_A, x), g.mat_mult(X.MAT_A, y)
+    assert abs(y @ Ax - x @ Ay) <= 1e-11 * (np.linalg.norm(x) * np.linalg.norm(Ay))
+    Az = g.mat_mult(X.MAT_A, 2.0 * x - 3.0 * y)
+    assert np.linalg.norm(Az - (2.0 * Ax - 3.0 * Ay)) <= 1e-12 * np.linalg.norm(Az)
+
+
+# ------------------------------------------------------------------ preconditioner pieces
+MG_CASES = [("3d_6_l3", 3, False, "-model 11 -size_x 0.1 -mx 6", 3), ("3d_8_l3_contrast", 3, False, "-model 6 -mx 8 -eta1 1e4", 3),
+            ("3d_noncubic_l2", 3, False, "-model 1 -mx 4 -my 6 -mz 2", 2), ("2d_16_l4", 2, False, "-model 0 -mx 16 -my 16 -size_y 0.1", 4),
+            ("lame3d_4_l2", 3, True, "-model 6 -mx 4 -lambda1 20", 2)]
+
+
+@pytest.fixture(scope="module", params=MG_CASES, ids=[c[0] for c in MG_CASES])
+def abf_pair(request):
+    _, nsd, lame, opts, levels = request.param
+    full = "%s %s -saddle_fieldsplit_u_pc_mg_levels %d -saddle_ksp_rtol 1e-8" % (ABF, opts, levels)
+    g = X.ExSaddle(full, nsd=nsd, lame=lame).assemble().ksp_setup()
+    o = O.Problem(full, nsd=nsd, lame=lame)
+    res = o.pc_setup()
+    yield g, o, res, levels
+    g.close()
+
+
+def test_galerkin_levels(abf_pair):
+    g, o, res, levels = abf_pair
+    for l in range(levels):
+        ia, ja, a, shape = g.mat_csr(X.MAT_MG_LEVEL0 + l)
+        L = o.mg_level(l)
+        assert shape == L.shape and np.array_equal(ia, L.ia) and np.array_equal(ja, L.ja)
+        assert _relerr(a, L.a) <= 1e-12
+        assert shape[0] == res.level_rows[l] and len(a) == res.level_nnz[l]
+
+
+def test_chebyshev_estimates_and_transfers(abf_pair):
+    g, o, res, levels = abf_pair
+    rng = np.random.default_rng(5)
+    for l in range(1, levels):
+        emin_est, emax_est, emin, emax = g.chebyshev(l)
+        assert abs(emax_est - res.cheb_emax_est[l]) <= 1e-9 * emax_est      # same rander48 noise vector by construction
+        assert abs(emin - res.cheb_emin[l]) <= 1e-9 * emax and abs(emax - res.cheb_emax[l]) <= 1e-9 * emax
+    for lc in range(levels - 1):
+        nf = g.mat_info(X.MAT_MG_LEVEL0 + lc + 1)[0]; nc = g.mat_info(X.MAT_MG_LEVEL0 + lc)[0]
+        rf = rng.standard_normal(nf); xc = rng.standard_normal(nc); xf = rng.standard_normal(nf)
+        assert _relerr(g.mg_restrict(lc, rf), o.restrict(lc, rf, nc)) <= 1e-14
+        assert _relerr(g.mg_interpolate_add(lc, xc, xf), o.prolong_add(lc, xc, xf.copy())) <= 1e-14
+
+
+def test_vcycle_ilu_and_fieldsplit_apply(abf_pair):
+    g, o, res, levels = abf_pair
+    rng = np.random.default_rng(11)
+    b = rng.standard_normal(o.nu)
+    bi, _ = o.bc(); b[bi] = 0.0
+    xg = g.pc_mg_apply(b); xo = o.vcycle(b)
+    assert np.linalg.norm(xg - xo) <= 1e-9 * np.linalg.norm(xo)
+    bp = rng.standard_normal(o.np_)
+    M = o.Mp(); lu = np.empty_like(M.a)
+    assert O.lib().xo_ilu0(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
+    xp = np.empty(o.np_); O.lib().xo_ilu0_solve(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(bp), O._dp(xp))
+    assert np.linalg.norm(g.pc_schur_apply(bp) - xp) <= 1e-12 * np.linalg.norm(xp)
+    r = o.F() + 1e-3 * rng.standard_normal(o.n) * np.linalg.norm(o.F()) / np.sqrt(o.n)
+    zg = g.pc_apply(r); zo, its = o.pc_apply(r)
+    assert np.linalg.norm(zg - zo) <= 1e-8 * np.linalg.norm(zo)
+
+
+def test_abf_solve_history_matches_oracle(abf_pair):
+    g, o, res, levels = abf_pair
+    x = g.solve()
+    xo, r = o.solve()
+    its, reason = g.iterations()
+    assert (its, reason) == (r.its, r.reason)
+    assert g.inner_iterations() == list(r.inner_its[:r.n_inner])
+    h = g.history(); ho = np.array(r.hist[:r.nhist])
+    assert len(h) == len(ho) and np.max(np.abs(h - ho) / ho) <= 1e-8
+    assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    # the answer really solves the system: true residual at the requested tolerance
+    F = o.F()
+    assert np.linalg.norm(F - o.mult(x)) <= 1.05e-8 * np.linalg.norm(F) * 1.5
+
+
+# ------------------------------------------------------------------ the reference's golden outputs, end to end
+def _run(kat, name, extra=""):
+    c = kat[name]
+    opts = c["options"].replace("-options_file abf.opts", ABF) + " " + extra
+    text, s, x = X.run_exsaddle(c["exe"], opts)
+    return c, text, s, x
+
+
+@pytest.mark.parametrize("name", ["exSaddle2d_1", "exSaddle3d_1"])
+def test_golden_jacobi_gmres_output_is_identical(kat, name):
+    """BASELINE config 0 (exSaddle2d_1) and the non-cubic 3-D case: the program output diffs clean against testref."""
+    c, text, s, x = _run(kat, name)
+    ref = open_ref_lines(c)
+    assert [l.rstrip() for l in text.rstrip("\n").split("\n")] == ref
+
+
+def open_ref_lines(c):
+    lines = list(c["banner"])
+    if "reason" in c:
+        verb = "converged" if c["reason"].startswith("CONVERGED") else "did not converge"
+        lines.append("Linear saddle_ solve %s due to %s iterations %d" % (verb, c["reason"], c["iterations"]))
+    lines += [l.rstrip() for l in c["diagnostics"]]
+    return lines
+
+
+@pytest.mark.parametrize("name", ["exSaddle3d_lame_3", "exSaddle3d_lame_4", "exSaddle3d_lame_5"])
+def test_golden_right_jacobi_histories(kat, name):
+    c, text, s, x = _run(kat, name)
+    h = s.history()
+    assert len(h) == len(c["residuals"])
+    for v, t in zip(h, c["residuals_text"]):
+        assert X.monitor_short(v) == t or abs(v - float(t)) <= 6e-6 * v
+    got = [l.rstrip() for l in text.rstrip("\n").split("\n") if l.startswith("|")]
+    assert got == [l.rstrip() for l in c["diagnostics"]]
+
+
+def test_golden_abf_pseudoice_history(kat):
+    c = kat["exSaddle3d_pseudoice_1"]
+    (a1, b1), (a2, b2) = c["cheb_bounds"][0], c["cheb_bounds"][1]
+    c, text, s, x = _run(kat, "exSaddle3d_pseudoice_1",
+                         "-saddle_fieldsplit_u_mg_levels_1_ksp_chebyshev_eigenvalues %r,%r -saddle_fieldsplit_u_mg_levels_2_ksp_chebyshev_eigenvalues %r,%r" % (a1, b1, a2, b2))
+    h = s.history()
+    assert s.iterations() == (20, 2) and len(h) == 21
+    for v, t in zip(h, c["residuals_text"]):
+        assert abs(v - float(t)) <= 1.2e-5 * v, (v, t)
+    # -ksp_view pins: level sizes and nnz
+    for l, (rows, nnz) in enumerate([(192, 9000), (1029, 61731), (6591, 1058841)]):
+        r, _, z, bs = s.mat_info(X.MAT_MG_LEVEL0 + l)
+        assert (r, z, bs) == (rows, nnz, 3)
+
+
+def test_golden_abf_ar_iteration_counts(kat):
+    c, text, s, x = _run(kat, "exSaddle3d_ar_1")
+    assert s.iterations()[0] == 6 and s.inner_iterations() == c["inner_its"]
+    for v, t in zip(s.history(), c["residuals"]):
+        assert abs(v - t) <= 3e-2 * t
+    assert s.options_left() == []     # "There are no unused options." (testref/exSaddle3d_ar_1.ref)
+
+
+# ------------------------------------------------------------------ larger sizes: properties instead of the oracle
+def test_32cubed_properties():
+    g = X.ExSaddle(ABF + " -mx 32 -model 6 -eta0 1 -eta1 100 -saddle_fieldsplit_u_pc_mg_levels 5 -saddle_ksp_rtol 1e-8", nsd=3).assemble()
+    m = 32
+    assert g.n == 3 * (2 * m + 1) ** 3 + (m + 1) ** 3 == 859812
+    assert g.nnz == 9 * (8 * m + 1) ** 3 + 2 * 3 * (5 * m + 1) ** 3 + (3 * m + 1) ** 3 == 178723696
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(g.n), rng.standard_normal(g.n)
+    Ax, Ay = g.mat_mult(X.MAT_A, x), g.mat_mult(X.MAT_A, y)
+    assert abs(y @ Ax - x @ Ay) <= 1e-11 * np.linalg.norm(x) * np.linalg.norm(Ay)
+    xu, xp = x[:g.nu], x[g.nu:]
+    yb = np.concatenate([g.mat_mult(X.MAT_A00, xu) + g.mat_mult(X.MAT_A01, xp), g.mat_mult(X.MAT_A10, xu) + g.mat_mult(X.MAT_A11, xp)])
+    assert np.linalg.norm(yb - Ax) <= 1e-12 * np.linalg.norm(Ax)
+    # constant pressure is in the kernel of the gradient block away from Dirichlet rows: sum over rows of A01 p=1
+    g.ksp_setup()
+    sol = g.solve()
+    its, reason = g.iterations()
+    assert reason == 2 and its < 60
+    F = g.rhs()
+    assert np.linalg.norm(F - g.mat_mult(X.MAT_A, sol)) <= 1.5e-8 * np.linalg.norm(F)
+    h = g.history()
+    assert abs(h[0] - np.linalg.norm(F)) <= 1e-12 * h[0] and np.all(h[1:] <= h[:-1] * (1 + 1e-12))   # FGMRES residual is monotone
+    g.close()

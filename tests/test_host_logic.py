@@ -1,0 +1,122 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every declared symbol,
+the integer index maps are bit-exact against the oracle, option handling and error behaviour mirror the
+reference (no compute calls: there is no GPU here and the library has no CPU path)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import exsaddle_b200 as X
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "exsaddle_b200.h")).read()
+    declared = set(re.findall(r"\b(xsb_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("xsb_ctx")
+    assert len(declared) >= 40
+    L = X.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "symbol %s declared in include/exsaddle_b200.h but not exported" % name
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "exsaddle_b200.h")).read()
+    assert "torch" not in hdr.replace("no torch", "") and "at::" not in hdr and "std::" not in hdr
+
+
+@pytest.mark.parametrize("nsd,m", [(2, (4, 4, 1)), (2, (3, 5, 1)), (3, (2, 2, 2)), (3, (4, 7, 5)), (3, (1, 1, 1)), (3, (3, 2, 4))])
+def test_pattern_rows_bit_exact_vs_oracle(nsd, m):
+    p = O.Problem("-mx %d -my %d -mz %d -model %d" % (m[0], m[1], m[2], 0), nsd=nsd)
+    A = p.A()
+    for row in range(p.n):
+        cols = X.pattern_row(nsd, m[0], m[1], m[2], row)
+        assert np.array_equal(cols, A.ja[A.ia[row]:A.ia[row + 1]]), row
+    assert X.prealloc_total(nsd, *m) == p.prealloc
+
+
+@pytest.mark.parametrize("nsd,lame,model,fs", [(2, 0, 0, 0), (2, 0, 0, 1), (3, 0, 0, 0), (3, 0, 0, 1), (3, 0, 11, 0), (3, 1, 8, 0),
+                                              (3, 1, 9, 0), (3, 1, 12, 0), (2, 1, 9, 0), (3, 1, 6, 0), (2, 0, 101, 0)])
+def test_bc_list_matches_oracle(nsd, lame, model, fs):
+    m = (4, 4, 4)
+    p = O.Problem("-mx 4 -model %d %s" % (model, "-freesliphack" if fs else ""), nsd=nsd, lame=bool(lame))
+    idx, val = X.bc_list(nsd, lame, model, fs, *m)
+    oi, ov = p.bc()
+    assert np.array_equal(idx, oi)
+    if model != 101:   # MMS values are filled from coordinates during assembly
+        assert np.array_equal(val, ov)
+
+
+def test_compression_quirk_noncubic():
+    """models.c:270 tests si+ni against the y count: on a non-square mesh the x-max face is not constrained."""
+    idx, val = X.bc_list(3, 1, 9, 0, 4, 3, 3)
+    p = O.Problem("-mx 4 -my 3 -mz 3 -model 9", nsd=3, lame=True)
+    assert np.array_equal(idx, p.bc()[0]) and len(idx) == 3 * 7 * 7
+
+
+def test_mg_level_dims_and_errors():
+    assert X.mg_level_dims(3, 6, 6, 6, 3, 2) == (13, 13, 13)
+    assert X.mg_level_dims(3, 6, 6, 6, 3, 1) == (7, 7, 7)
+    assert X.mg_level_dims(3, 6, 6, 6, 3, 0) == (4, 4, 4)
+    assert X.mg_level_dims(2, 32, 32, 1, 3, 0) == (17, 17, 1)
+    assert X.mg_level_dims(3, 64, 64, 64, 6, 0) == (5, 5, 5)
+    with pytest.raises(X.XsbError):
+        X.mg_level_dims(3, 6, 6, 6, 4, 0)     # 4 nodes cannot be coarsened again
+
+
+def test_slab_ranges_partition_the_mesh():
+    for mz, P in [(128, 8), (64, 4), (10, 3), (7, 7)]:
+        rs = [X.slab_range(mz, P, r) for r in range(P)]
+        assert rs[0][0] == 0 and rs[-1][1] == mz
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(P - 1))
+        sizes = [b - a for a, b in rs]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(X.XsbError):
+        X.slab_range(3, 4, 0)
+
+
+def test_options_and_banner_without_device(kat):
+    c = kat["exSaddle3d_ar_1"]
+    s = X.ExSaddle(nsd=3)
+    s.set_options(c["options"].replace("-options_file abf.opts", " ".join(kat["_abf_opts"])))
+    assert s.banner().rstrip("\n").split("\n") == c["banner"]
+    s2 = X.ExSaddle("-model 6 -mx 4", nsd=3, lame=True)
+    assert s2.banner().rstrip("\n").split("\n") == kat["exSaddle3d_lame_1"]["banner"]
+    s3 = X.ExSaddle("-model 11 -size_x 0.1 -mx 6", nsd=3)
+    assert s3.banner().rstrip("\n").split("\n") == kat["exSaddle3d_pseudoice_1"]["banner"]
+
+
+def test_unsupported_models_error_like_reference():
+    with pytest.raises(X.XsbError) as e:
+        X.ExSaddle("-model 3", nsd=3).banner()
+    assert "not implemented" in str(e.value)          # models.c:1521
+    with pytest.raises(X.XsbError) as e:
+        X.ExSaddle("-model 2 -sinker_n 9", nsd=3).banner()
+    assert "Too many sinkers" in str(e.value)         # models.c:1041
+    with pytest.raises(X.XsbError) as e:
+        X.ExSaddle("-model 2 -sinker_r 0.06", nsd=3).banner()
+    assert "Sinker Radius too big" in str(e.value)    # models.c:1044
+
+
+@pytest.mark.skipif(X.device_available(), reason="checks the no-GPU behaviour")
+def test_compute_calls_fail_loudly_without_gpu():
+    s = X.ExSaddle("-mx 2 -model 0", nsd=3)
+    with pytest.raises(X.XsbError) as e:
+        s.assemble()
+    assert e.value.code == -6 and "no CPU path" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under exsaddle_b200/ or include/ may reference it."""
+    for d in ("exsaddle_b200", "include"):
+        for root, _, files in os.walk(os.path.join(ROOT, d)):
+            if "build" in root.split(os.sep) or "__pycache__" in root:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
+                    txt = open(os.path.join(root, f)).read()
+                    assert "oracle" not in txt.lower().replace("no oracle", ""), os.path.join(root, f)
+                    assert "libxo" not in txt and "xo_" not in txt, os.path.join(root, f)
