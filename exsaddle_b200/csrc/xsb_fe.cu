@@ -630,7 +630,7 @@ int fe_assemble(xsb_ctx c)
     a00_len_kernel<<<nblk(L.nun), 256, 0, st>>>(L, len64); KERNEL_OK();
     Baij &B = c->A00; B.nb = (int)L.nun; B.bs = nsd; B.pat = BoxPattern{L.NX, L.NY, L.NZ, 1};
     { int rc = scan_to_ia(c, L.nun, len64, &B.ia, &B.nblk); if (rc) { cudaFree(len64); return rc; } }
-    XSB_CHK(dev_alloc(c, &B.ja, (size_t)B.nblk)); XSB_CHK(dev_alloc(c, &B.a, (size_t)B.nblk * nsd * nsd));
+    XSB_CHK(dev_alloc(c, &B.ja, (size_t)B.nblk)); XSB_CHK(dev_alloc(c, &B.a, (size_t)B.nblk * nsd * nsd + 2));   // +2: the tile kernel's last 16-byte load may straddle the end
     a00_fill_kernel<<<nblk(L.nun * 32), 256, 0, st>>>(L, c->A.ia, c->A.ja, c->A.a, B.ia, B.ja, B.a); KERNEL_OK();
     struct { Csr *S; int64_t r0, nr; int pcols; } subs[3] = {{&c->A01, 0, L.nu, 1}, {&c->A10, L.nu, L.np, 0}, {&c->A11, L.nu, L.np, 1}};
     for (auto &s : subs) {

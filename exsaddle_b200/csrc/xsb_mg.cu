@@ -136,7 +136,7 @@ static int galerkin(xsb_ctx c, const Level &F, Level &C)
   int64_t tot = 0; CUDA_OK(cudaMemcpyAsync(&tot, len + ncn, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(tmp));
   Baij &A = C.A; A.nb = (int)ncn; A.bs = bs; A.nblk = tot; A.pat = cp;
-  XSB_CHK(dev_alloc(c, &A.ia, (size_t)ncn + 1)); XSB_CHK(dev_alloc(c, &A.ja, (size_t)tot)); XSB_CHK(dev_alloc(c, &A.a, (size_t)tot * bs * bs));
+  XSB_CHK(dev_alloc(c, &A.ia, (size_t)ncn + 1)); XSB_CHK(dev_alloc(c, &A.ja, (size_t)tot)); XSB_CHK(dev_alloc(c, &A.a, (size_t)tot * bs * bs + 2));
   k_narrow<<<nblk(ncn + 1), 256, 0, st>>>(ncn, len, A.ia); KERNEL_OK();
   if (bs == 3) k_galerkin<3><<<nblk(ncn * 27, 128), 128, 0, st>>>(F.A.pat, F.A.ia, F.A.a, cp, A.ia, A.ja, A.a);
   else k_galerkin<2><<<nblk(ncn * 27, 128), 128, 0, st>>>(F.A.pat, F.A.ia, F.A.a, cp, A.ia, A.ja, A.a);

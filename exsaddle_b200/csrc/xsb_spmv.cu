@@ -5,11 +5,10 @@
 //   spmv_csr   AIJ layout (the reference's MATAIJ): one warp per row, lanes stride the row so every
 //              load instruction of values / column indices is a contiguous 256 B / 128 B segment;
 //              matrix stream uses ld.global.cs (evict-first) so the 126 MB L2 stays available for x.
-//   spmv_baij  BAIJ(bs) velocity block A00 and every Galerkin level: one warp per block row, lanes stride
-//              the row's bs*bs*nblocks doubles flat (coalesced), block column index broadcast from L1,
-//              three per-component accumulators reduced by warp shuffles.  The epilogue fuses the vector
-//              work that always follows the product in the smoother (residual / Chebyshev update), so the
-//              smoother makes exactly one pass over A00 per iteration and no separate vector passes.
+//   spmv_baij  BAIJ(bs) velocity block A00 and every Galerkin level: one warp per block row with fixed lane
+//              roles (see the kernel).  The epilogue fuses the vector work that always follows the product in
+//              the smoother (residual / Chebyshev update), so the smoother makes exactly one pass over A00
+//              per iteration and no separate vector passes.
 #include "xsb.h"
 
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
@@ -53,67 +52,59 @@ int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y)
   int64_t blocks = (warps * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;   // persistent-style grid: 148 SMs x 8 resident CTAs x 16 waves
   if (blocks > cap) blocks = cap;
-  spmv_csr_kernel<4><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, x, y); KERNEL_OK();
+  spmv_csr_kernel<8><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, x, y); KERNEL_OK();
   return XSB_OK;
 }
 
-// ------------------------------------------------------------------ K2: BAIJ with fused epilogue
-template <int BS>
-__device__ __forceinline__ void epilogue_store(const Epilogue &ep, int64_t node, int lane, const double (&acc)[3], double *__restrict__ y)
+// ------------------------------------------------------------------ K2: BAIJ with fixed lane roles, fused epilogue
+__device__ __forceinline__ double epilogue_value(const Epilogue &ep, int64_t i, double ax)
 {
-  // lanes 0..BS-1 each finish one component of the block row
-  if (lane < BS) {
-    const int64_t i = (int64_t)BS * node + lane;
-    const double ax = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
-    double out;
-    switch (ep.mode) {
-    case EPI_RESIDUAL:   out = ep.b[i] - ax; break;                                         // r = b - A x
-    case EPI_CHEB_FIRST: out = ep.pk[i] + ep.s0 * (ep.idiag[i] * (ep.b[i] - ax)); break;    // p1 = x + scale*B(b - A x)
-    case EPI_CHEB:       out = ep.s0 * ep.pkm1[i] + ep.s1 * ep.pk[i] + ep.s2 * (ep.idiag[i] * (ep.b[i] - ax)); break; // VecAXPBYPCZ
-    default:             out = ax;
-    }
-    y[i] = out;
+  switch (ep.mode) {
+  case EPI_RESIDUAL:   return ep.b[i] - ax;                                                             // r = b - A x
+  case EPI_CHEB_FIRST: return ep.pk[i] + ep.s0 * (ep.idiag[i] * (ep.b[i] - ax));                        // p1 = x + scale*B(b - A x)
+  case EPI_CHEB:       return ep.s0 * ep.pkm1[i] + ep.s1 * ep.pk[i] + ep.s2 * (ep.idiag[i] * (ep.b[i] - ax)); // VecAXPBYPCZ
+  default:             return ax;
   }
 }
 
-template <int BS>
+// One warp per block row.  Each lane keeps a FIXED role (block g of the group, row comp ra, col comp ca) for the
+// whole kernel: a warp iteration consumes NBW = 32/BS^2 whole blocks (27 of 32 lanes for BS = 3, all 32 for BS = 2)
+// with one coalesced value load, one block-column load, one x gather and one FMA per lane -- no per-element
+// div/mod, a single accumulator.  UN iterations are issued back to back so UN loads per lane are in flight.
+template <int BS, int UN>
 __global__ void __launch_bounds__(256) spmv_baij_kernel(int nb, const int *__restrict__ ia, const int *__restrict__ ja,
                                                         const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y, Epilogue ep)
 {
-  constexpr int BS2 = BS * BS;
+  constexpr int BS2 = BS * BS, NBW = 32 / BS2, ACTIVE = NBW * BS2;
   const int lane = threadIdx.x & 31;
+  const int g = lane / BS2, r = lane - g * BS2, ra = r / BS, ca = r - ra * BS;
+  const bool active = lane < ACTIVE;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t node = warp; node < nb; node += nwarps) {
     const int b0 = ia[node], nblk = ia[node + 1] - b0;
-    const int len = nblk * BS2;
-    const double *__restrict__ av = a + (int64_t)b0 * BS2;
-    const int *__restrict__ cj = ja + b0;
-    double acc[3] = {0.0, 0.0, 0.0};
-    // element t of the flat block row: block t/BS2, entry r = t%BS2 = (row comp r/BS, col comp r%BS)
-    int t = lane, blk = lane / BS2, r = lane - blk * BS2;
-    constexpr int DB = 32 / BS2, DR = 32 - DB * BS2;   // t += 32  =>  blk += DB, r += DR (mod BS2)
-    for (; t + 96 < len; t += 128) {
-      double v[4]; int bb[4], rr[4];
+    const double *__restrict__ av = a + (int64_t)b0 * BS2 + lane;
+    const int *__restrict__ cj = ja + b0 + g;
+    const int mine = active ? (nblk - g + NBW - 1) / NBW : 0;   // iterations in which this lane's block exists
+    double acc = 0.0;
+    for (int it = 0; it < mine; it += UN) {
+      double v[UN]; int col[UN];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        v[u] = ld_stream(av + t + 32 * u); bb[u] = blk; rr[u] = r;
-        blk += DB; r += DR; if (r >= BS2) { r -= BS2; blk += 1; }
+      for (int u = 0; u < UN; ++u) {
+        const bool ok = it + u < mine;
+        v[u] = ok ? ld_stream(av + (int64_t)(it + u) * ACTIVE) : 0.0;
+        col[u] = ok ? __ldg(cj + (it + u) * NBW) : 0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int ra = rr[u] / BS, ca = rr[u] - ra * BS;
-        const double p = v[u] * __ldg(x + (int64_t)BS * __ldg(cj + bb[u]) + ca);
-        acc[0] += ra == 0 ? p : 0.0; acc[1] += ra == 1 ? p : 0.0; if (BS == 3) acc[2] += ra == 2 ? p : 0.0;
-      }
+      for (int u = 0; u < UN; ++u) acc += v[u] * __ldg(x + (int64_t)BS * col[u] + ca);
     }
-    for (; t < len; t += 32) {
-      const int ra = r / BS, ca = r - ra * BS;
-      const double p = ld_stream(av + t) * __ldg(x + (int64_t)BS * __ldg(cj + blk) + ca);
-      acc[0] += ra == 0 ? p : 0.0; acc[1] += ra == 1 ? p : 0.0; if (BS == 3) acc[2] += ra == 2 ? p : 0.0;
-      blk += DB; r += DR; if (r >= BS2) { r -= BS2; blk += 1; }
-    }
-    acc[0] = warp_sum(acc[0]); acc[1] = warp_sum(acc[1]); if (BS == 3) acc[2] = warp_sum(acc[2]);
-    epilogue_store<BS>(ep, node, lane, acc, y);
+    // sum over the column component (lanes r, r+1, ..), then over the NBW block slots
+    double t = acc;
+#pragma unroll
+    for (int s = 1; s < BS; ++s) t += __shfl_down_sync(0xffffffffu, acc, s);
+    double tot = t;
+#pragma unroll
+    for (int s = 1; s < NBW; ++s) tot += __shfl_down_sync(0xffffffffu, t, s * BS2);
+    if (g == 0 && ca == 0 && active) { const int64_t i = (int64_t)BS * node + ra; y[i] = epilogue_value(ep, i, tot); }
   }
 }
 
@@ -123,8 +114,8 @@ int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilog
   const int tpb = 256; int64_t blocks = ((int64_t)A.nb * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;
   if (blocks > cap) blocks = cap;
-  if (A.bs == 3) spmv_baij_kernel<3><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
-  else if (A.bs == 2) spmv_baij_kernel<2><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
+  if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
+  else if (A.bs == 2) spmv_baij_kernel<2, 4><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
   else return xsb_fail(c, XSB_ERR_SUP, "BAIJ block size %d", A.bs);
   KERNEL_OK();
   return XSB_OK;

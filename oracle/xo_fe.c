@@ -640,7 +640,7 @@ static int build_pattern(xo_problem *P)
 
 static inline int find_col(const int *ja, int lo, int hi, int col)
 {
-  while (lo < hi) { int mid = (lo + hi) >> 1; if (ja[mid] < col) lo = mid + 1; else hi = mid; }
+  while (lo < hi) { int mid = lo + ((hi - lo) >> 1); if (ja[mid] < col) lo = mid + 1; else hi = mid; }   /* lo+hi would overflow int at 64^3 */
   return lo;
 }
 
