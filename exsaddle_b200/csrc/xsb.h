@@ -146,7 +146,8 @@ struct xsb_ctx_s {
   double *idiagA = nullptr;
   // solver state
   int nlev = 0; Level lev[XSB_MAX_LEVELS];
-  double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr; int ilu_nlvl = 0;
+  double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr, *ilu_diag = nullptr; int ilu_nlvl = 0;
+  int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
   double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr;
