@@ -124,6 +124,7 @@ struct SolverOpts {
   int n_cheb_fixed = 0; double cheb_emin[XSB_MAX_LEVELS], cheb_emax[XSB_MAX_LEVELS];
   int p_pc = 0;          // 0 ilu0 (bjacobi) 1 jacobi
   int time_kernels = 0;
+  int matrix_free = 0;   // -xsb_matrix_free: fine-level A00 products by the sum-factorised element kernel (xsb_mf.cu)
 };
 
 struct xsb_ctx_s {
@@ -150,7 +151,7 @@ struct xsb_ctx_s {
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
-  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr;
+  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr;
   double *red = nullptr;      // device reduction scratch
   double *red_h = nullptr;    // pinned host mirror
   double *scal = nullptr;     // device scalars (dot results consumed by kernels)
@@ -183,6 +184,9 @@ int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y);
 int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);
 int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);   // counted (+ timed) fine-level launch
 int spmv_collect_timing(xsb_ctx c);
+// ---- xsb_mf.cu
+int mf_setup(xsb_ctx c);
+int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep);
 // ---- xsb_vec.cu
 int vec_set(xsb_ctx c, int64_t n, double a, double *x);
 int vec_copy(xsb_ctx c, int64_t n, const double *x, double *y);

@@ -177,7 +177,7 @@ static int pick_csr(xsb_ctx c, int which, const Csr **S, const Baij **B)
   if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "matrix requested before xsb_assemble");
   switch (which) {
   case XSB_MAT_A: *S = &c->A; return 0;
-  case XSB_MAT_A00: *B = &c->A00; return 0;
+  case XSB_MAT_A00: case XSB_MAT_A00_MF: *B = &c->A00; return 0;
   case XSB_MAT_A01: *S = &c->A01; return 0;
   case XSB_MAT_A10: *S = &c->A10; return 0;
   case XSB_MAT_A11: *S = &c->A11; return 0;
@@ -216,7 +216,9 @@ int xsb_mat_mult_dev(xsb_ctx c, int which, const double *x, double *y)
   NEED_DEVICE(c);
   const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
   if (S) return spmv_csr(c, *S, x, y);
-  Epilogue ep; return spmv_baij(c, *B, x, y, ep);
+  Epilogue ep;
+  if (which == XSB_MAT_A00_MF) { XSB_CHK(mf_setup(c)); return mf_a00_apply(c, x, y, ep); }
+  return spmv_baij(c, *B, x, y, ep);
 }
 
 int xsb_mat_mult(xsb_ctx c, int which, const double *x, double *y)

@@ -163,6 +163,7 @@ static int read_solver_options(xsb_ctx c)
   if (ppc == "bjacobi" || ppc == "ilu") s.p_pc = 0; else if (ppc == "jacobi") s.p_pc = 1;
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_fieldsplit_p_pc_type %s not supported (bjacobi|ilu|jacobi)", ppc.c_str());
   s.time_kernels = o.flag("xsb_time_kernels");
+  s.matrix_free = o.flag("xsb_matrix_free");
   if (s.restart < 1 || s.restart > 60 || s.u_restart < 1 || s.u_restart > 60) return xsb_fail(c, XSB_ERR_ARG, "restart must be in [1,60]");
   // monitor / view flags of the reference's command lines are accepted and handled by the caller
   o.has("saddle_ksp_monitor_short"); o.has("saddle_ksp_converged_reason"); o.has("saddle_ksp_view"); o.has("diagnostics");
@@ -180,6 +181,7 @@ int ksp_setup(xsb_ctx c)
   if (!c->w_t1) { XSB_CHK(dev_alloc(c, &c->w_t1, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->w_t2, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->xdev, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->bdev, (size_t)L.n)); }
   if (c->so.pc_type == 1) { XSB_CHK(dev_alloc(c, &c->idiagA, (size_t)L.n)); XSB_CHK(csr_diag_inv(c, c->A, c->idiagA)); }
   if (c->so.pc_type == 2) {
+    if (c->so.matrix_free) XSB_CHK(mf_setup(c));
     XSB_CHK(mg_setup(c));
     if (c->so.p_pc == 0) XSB_CHK(ilu_setup(c));
     else { XSB_CHK(dev_alloc(c, &c->mp_idiag, (size_t)L.np)); XSB_CHK(csr_diag_inv(c, c->Mp, c->mp_idiag)); }

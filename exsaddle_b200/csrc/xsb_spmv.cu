@@ -132,7 +132,7 @@ int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Ep
     if (c->ev_used + 2 > c->evpool.size()) { for (int i = 0; i < 256; ++i) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); c->evpool.push_back(e); } }
     CUDA_OK(cudaEventRecord(c->evpool[c->ev_used], c->stream));
   }
-  XSB_CHK(spmv_baij(c, A, x, y, ep));
+  if (c->so.matrix_free) XSB_CHK(mf_a00_apply(c, x, y, ep)); else XSB_CHK(spmv_baij(c, A, x, y, ep));
   if (timed) { CUDA_OK(cudaEventRecord(c->evpool[c->ev_used + 1], c->stream)); c->ev_used += 2; }
   return XSB_OK;
 }

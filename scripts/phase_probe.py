@@ -8,7 +8,7 @@ mx, eta1, levels = int(sys.argv[1]), float(sys.argv[2]), int(sys.argv[3])
 maxit = int(sys.argv[4]) if len(sys.argv) > 4 else 200
 class A: pass
 a = A(); a.mx, a.eta1, a.levels = mx, eta1, levels
-opts = bench.workload_options(a) + " -saddle_ksp_max_it %d -xsb_time_kernels" % maxit
+opts = bench.workload_options(a) + " -saddle_ksp_max_it %d -xsb_time_kernels %s" % (maxit, " ".join(sys.argv[5:]))
 g = X.ExSaddle(opts, nsd=3)
 t = time.time(); g.assemble(); print("assemble %.3f s" % (time.time() - t), g.n, g.nnz, flush=True)
 t = time.time(); g.ksp_setup(); print("ksp_setup %.3f s" % (time.time() - t), flush=True)

@@ -263,3 +263,32 @@ def test_32cubed_properties():
     h = g.history()
     assert abs(h[0] - np.linalg.norm(F)) <= 1e-12 * h[0] and np.all(h[1:] <= h[:-1] * (1 + 1e-12))   # FGMRES residual is monotone
     g.close()
+
+
+# ------------------------------------------------------------------ K4: matrix-free Q2 apply
+@pytest.mark.parametrize("opts,lame", [("-model 6 -mx 4 -eta1 1e4", False), ("-model 1 -mx 3 -my 5 -mz 2 -eta1 10", False),
+                                       ("-model 11 -size_x 0.1 -mx 6", False), ("-model 0 -mx 5 -size_z 0.3 -freesliphack", False),
+                                       ("-model 12 -mx 4 -mu1 10", True), ("-model 2 -mx 1", False)])
+def test_matrix_free_apply_matches_assembled_block(opts, lame):
+    g = X.ExSaddle(opts, nsd=3, lame=lame).assemble()
+    o = O.Problem(opts, nsd=3, lame=lame)
+    A00 = o.submatrix(0, 0).scipy()
+    rng = np.random.default_rng(2)
+    for x in (np.sin(0.37 * np.arange(o.nu)) + 0.1, rng.standard_normal(o.nu)):
+        y = g.mat_mult(X.MAT_A00_MF, x)
+        yo = A00 @ x
+        assert np.linalg.norm(y - yo) <= 1e-12 * np.linalg.norm(yo)
+        assert np.linalg.norm(y - g.mat_mult(X.MAT_A00, x)) <= 1e-12 * np.linalg.norm(yo)
+    g.close()
+
+
+def test_matrix_free_solve_matches_assembled_solve():
+    base = ABF + " -model 6 -mx 8 -eta1 1e4 -saddle_ksp_rtol 1e-8"
+    ga = X.ExSaddle(base, nsd=3).assemble().ksp_setup()
+    gm = X.ExSaddle(base + " -xsb_matrix_free", nsd=3).assemble().ksp_setup()
+    xa, xm = ga.solve(), gm.solve()
+    assert ga.iterations() == gm.iterations() and ga.inner_iterations() == gm.inner_iterations()
+    ha, hm = ga.history(), gm.history()
+    assert np.max(np.abs(ha - hm)) <= 1e-10 * ha[0]
+    assert np.linalg.norm(xa - xm) <= 1e-7 * np.linalg.norm(xa)
+    ga.close(); gm.close()
