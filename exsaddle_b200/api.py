@@ -56,6 +56,8 @@ def lib():
             "xsb_bc_list": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int],
             "xsb_mg_level_dims": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
             "xsb_slab_range": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+            "xsb_slab_layout": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64p],
+            "xsb_comm_unique_id": [C.c_char_p], "xsb_comm_init": [vp, C.c_char_p, C.c_int, C.c_int], "xsb_get_partition": [vp, i64p],
         }
         for name, args in sig.items():
             f = getattr(L, name); f.argtypes = args; f.restype = C.c_int
@@ -115,6 +117,25 @@ def slab_range(mz, nranks, rank):
     return a.value, b.value
 
 
+_PART_KEYS = ("rank", "nranks", "k0", "k1", "e0", "e1", "u_off", "u_len", "p_off", "p_len", "u_glob0", "p_glob0")
+
+
+def slab_layout(nsd, mx, my, mz, nranks, rank):
+    out = (C.c_int64 * 12)()
+    rc = lib().xsb_slab_layout(nsd, mx, my, mz, nranks, rank, out)
+    if rc:
+        raise XsbError(rc, "bad slab layout request")
+    return dict(zip(_PART_KEYS, [int(v) for v in out]))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    rc = lib().xsb_comm_unique_id(buf)
+    if rc:
+        raise XsbError(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
 class ExSaddle:
     """One exSaddle{2d,3d}{,_lame} run on the GPU. `opts` is the reference's own option string."""
 
@@ -152,6 +173,15 @@ class ExSaddle:
         buf = C.create_string_buffer(1 << 16)
         self._chk(self.L.xsb_options_left(self.h, buf, len(buf)))
         return [l for l in buf.value.decode().split("\n") if l]
+
+    # multi-GPU ----------------------------------------------------------------------------------------
+    def comm_init(self, unique_id, rank, nranks):
+        self._chk(self.L.xsb_comm_init(self.h, unique_id, rank, nranks)); return self
+
+    def partition(self):
+        out = (C.c_int64 * 12)()
+        self._chk(self.L.xsb_get_partition(self.h, out))
+        return dict(zip(_PART_KEYS, [int(v) for v in out]))
 
     # FE set-up ----------------------------------------------------------------------------------------
     def assemble(self):

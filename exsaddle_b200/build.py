@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexsaddle_b200.so")
-SOURCES = ["xsb_api.cu", "xsb_fe.cu", "xsb_spmv.cu", "xsb_vec.cu", "xsb_mg.cu", "xsb_ilu.cu", "xsb_ksp.cu", "xsb_mf.cu"]
+SOURCES = ["xsb_api.cu", "xsb_fe.cu", "xsb_spmv.cu", "xsb_vec.cu", "xsb_mg.cu", "xsb_ilu.cu", "xsb_ksp.cu", "xsb_mf.cu", "xsb_comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -40,7 +40,7 @@ def build(verbose=False, force=False, ptxas_info=False):
                 raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + out)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-cudart", "static"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-cudart", "static", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode:
             raise RuntimeError("link failed:\n" + r.stdout)

@@ -27,12 +27,24 @@ enum { BC_SOLCX = 0, BC_FIXEDBASE, BC_COMPRESSION, BC_COMPRESSION2, BC_MMS1 };
 // Lattice description shared by host and device code.
 struct Lattice {
   int nsd;
-  int mx, my, mz;          // elements (mz = 1 in 2-D)
+  int mx, my, mz;          // elements of the LOCAL lattice (mz = 1 in 2-D)
   int NX, NY, NZ;          // velocity nodes
   int PX, PY, PZ;          // pressure nodes
   int64_t nun, npn, nu, np, n, nel;
-  double hu[3];            // velocity node spacing
+  double hu[3];            // velocity node spacing (from the GLOBAL mesh)
+  int zoff;                // first element layer of the local lattice in the global mesh (0 on one GPU)
 };
+
+// z-slab partition: this rank owns element layers [k0,k1) of mz_glob and works on the local lattice
+// of layers [e0,e1) = [k0-2, k1+1) clipped to the mesh, so that every matrix row of an owned node, and every
+// row one node plane below (needed by the Galerkin product), is complete without communication.
+struct Slab {
+  int rank = 0, nranks = 1, mz_glob = 0;
+  int k0 = 0, k1 = 0, e0 = 0, e1 = 0;
+  int ou0 = 0, ou1 = 0;    // owned velocity-node planes, local indices [ou0,ou1)
+  int op0 = 0, op1 = 0;    // owned pressure-node planes
+};
+struct Ranges { int64_t off0 = 0, len0 = 0, off1 = 0, len1 = 0; };   // owned index ranges of a ghosted vector
 
 // Coupling ranges along one direction. i = node coordinate, N = nodes in that direction.
 // velocity node -> velocity nodes: +-2 from an element-corner (even) node, +-1 from a mid (odd) node.
@@ -96,6 +108,7 @@ struct Level {
   double emin = 0, emax = 0, emin_est = NAN, emax_est = NAN;
   double *x = nullptr, *b = nullptr, *r = nullptr, *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
   double *inv = nullptr;      // dense inverse of the coarsest operator
+  bool dist = false;          // z-slab distributed level (vectors on the local lattice, ghost planes, owned-row products)
 };
 
 struct Options {
@@ -141,7 +154,7 @@ struct xsb_ctx_s {
   double *coeff = nullptr;       // [slot][nel*nqp]
   double *coeff_nodal = nullptr; // [slot][npn]
   int nbc = 0; int *bc_idx = nullptr; double *bc_val = nullptr; unsigned char *isbc = nullptr;
-  Csr A, A01, A10, A11, Mp;
+  Csr A, A01, A10, A11, Mp, MpOwn;   // MpOwn: this rank's diagonal block of Mp (bjacobi); = Mp on one GPU
   Baij A00;
   double *F = nullptr;
   double *idiagA = nullptr;
@@ -162,6 +175,8 @@ struct xsb_ctx_s {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   std::vector<cudaEvent_t> evpool; size_t ev_used = 0;   // event pairs around fine-level A00 launches (-xsb_time_kernels)
   int64_t a00_mode[4] = {0, 0, 0, 0};                    // fine-level A00 launches per epilogue mode
+  Slab slab; void *nccl = nullptr;          // ncclComm_t when nranks > 1
+  Ranges own_full, own_u, own_p;            // owned entries of [u|p], u and p vectors on the local lattice
   std::vector<void *> allocs;   // every device allocation, for xsb_reset
   void *fe_tables = nullptr;    // FeTables on the device
 };
@@ -177,11 +192,12 @@ int dev_free_all(xsb_ctx c);
 // ---- xsb_fe.cu
 int fe_resolve_model(xsb_ctx c);
 int fe_assemble(xsb_ctx c);
+int bc_list_faces(int nsd, int lame, int model, int freeslip, int mx, int my, int mz, int zlo, int zhi, int32_t *idx, double *val, int cap);
 // ---- xsb_spmv.cu
 enum { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_CHEB_FIRST = 2, EPI_CHEB = 3 };
 struct Epilogue { int mode = EPI_PLAIN; const double *b = nullptr, *idiag = nullptr, *pk = nullptr, *pkm1 = nullptr; double s0 = 0, s1 = 0, s2 = 0; };
-int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y);
-int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);
+int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0 = 0, int64_t nrows = -1);
+int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0 = 0, int nnodes = -1);
 int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);   // counted (+ timed) fine-level launch
 int spmv_collect_timing(xsb_ctx c);
 // ---- xsb_mf.cu
@@ -195,14 +211,25 @@ int vec_aypx(xsb_ctx c, int64_t n, double a, const double *x, double *y);       
 int vec_scale(xsb_ctx c, int64_t n, double a, double *x);
 int vec_pmult(xsb_ctx c, int64_t n, const double *d, const double *x, double *y);    // y = d .* x
 int vec_waxpy(xsb_ctx c, int64_t n, double a, const double *x, const double *y, double *w); // w = y + a x
-int vec_mdot(xsb_ctx c, int64_t n, const double *w, double *const *V, int k, bool with_norm, double *out_dev); // out[j] = w.V[j], out[k] = w.w
+int vec_mdot(xsb_ctx c, const Ranges &rg, const double *w, double *const *V, int k, bool with_norm, double *out_dev); // out[j] = w.V[j], out[k] = w.w (owned entries, all ranks)
 int vec_maxpy_dev(xsb_ctx c, int64_t n, double *w, double *const *V, int k, const double *coef_dev, double sign); // w += sign * sum coef[j] V[j]
 int vec_maxpy_host(xsb_ctx c, int64_t n, double *w, double *const *V, int k, const double *coef_host);
 int vec_scale_by_inv_sqrt(xsb_ctx c, int64_t n, double *w, const double *nrm2_dev);  // w /= sqrt(*nrm2)
-int vec_gcr_update(xsb_ctx c, int64_t n, const double *dots_dev /* [r.v, v.v] */, double *v, double *s, double *x, double *r, double *rnorm2_dev);
+int vec_gcr_update(xsb_ctx c, const Ranges &rg, const double *dots_dev /* [r.v, v.v] */, double *v, double *s, double *x, double *r, double *rnorm2_dev);
 int vec_fetch(xsb_ctx c, const double *dev, int n, double *host);   // sync copy of n scalars
 int vec_diagnostics(xsb_ctx c, const double *x, double *out);
-int vec_rander48(xsb_ctx c, int64_t n, int interval, double *x);
+int vec_rander48(xsb_ctx c, int64_t n, int interval, double *x, int64_t stream_offset = 0);
+// ---- xsb_comm.cu
+int comm_init(xsb_ctx c, const void *unique_id, int rank, int nranks);
+int comm_unique_id(void *out128);
+int comm_destroy(xsb_ctx c);
+int comm_allreduce_sum(xsb_ctx c, double *dev, int n);
+int comm_halo_u(xsb_ctx c, double *u);            // fill the velocity ghost planes owned rows read (2 below, 1 above)
+int comm_halo_p(xsb_ctx c, double *p);            // pressure ghost planes (1 below, 1 above)
+int comm_halo_full(xsb_ctx c, double *x);         // [u|p]
+int comm_bcast_segments(xsb_ctx c, double *glob, const int64_t *offs /* nranks+1 */);
+int comm_bcast_planes(xsb_ctx c, double *glob, int64_t plane_doubles, int nplanes_glob);   // every rank contributes its owned coarse planes
+inline Ranges whole(int64_t n) { Ranges r; r.len0 = n; return r; }
 // ---- xsb_mg.cu
 int mg_setup(xsb_ctx c);
 int mg_vcycle(xsb_ctx c, const double *b, double *x);
@@ -215,6 +242,7 @@ int ilu_setup(xsb_ctx c);
 int ilu_apply(xsb_ctx c, const double *b, double *x);
 // ---- xsb_ksp.cu
 int ksp_setup(xsb_ctx c);
+int op_full_mult(xsb_ctx c, const double *x, double *y);
 int ksp_solve(xsb_ctx c, const double *b_dev, double *x_dev);
 int pc_apply(xsb_ctx c, const double *r, double *z, int *inner);
 int hess_eig(int n, const double *H, int ldh, double *wr, double *wi);

@@ -17,6 +17,7 @@ template <class T> int dev_alloc(xsb_ctx c, T **p, size_t n)
   void *q = nullptr; if (n == 0) n = 1;
   cudaError_t e = cudaMalloc(&q, n * sizeof(T));
   if (e != cudaSuccess) return xsb_fail(c, XSB_ERR_MEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  cudaMemsetAsync(q, 0, n * sizeof(T), c->stream);   // ghost entries of slab vectors must be finite
   c->allocs.push_back(q); *p = (T *)q;
   return 0;
 }
@@ -64,10 +65,12 @@ int xsb_reset(xsb_ctx c)
   if (!c) return XSB_ERR_ARG;
   if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
   Options opt = c->opt; int nsd = c->nsd, lame = c->lame, device = c->device; bool hd = c->have_device;
+  const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl;
   cudaStream_t st = c->stream; cudaEvent_t e0 = c->ev0, e1 = c->ev1, k0 = c->evk0, k1 = c->evk1;
   *c = xsb_ctx_s();
   c->opt = opt; c->opt.used.clear(); c->nsd = nsd; c->lame = lame; c->device = device; c->have_device = hd;
   c->stream = st; c->ev0 = e0; c->ev1 = e1; c->evk0 = k0; c->evk1 = k1;
+  c->slab.rank = rank; c->slab.nranks = nranks; c->nccl = nccl;
   return XSB_OK;
 }
 
@@ -76,6 +79,7 @@ int xsb_destroy(xsb_ctx *pc)
   if (!pc || !*pc) return XSB_OK;
   xsb_ctx c = *pc;
   xsb_reset(c);
+  comm_destroy(c);
   if (c->have_device) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1); cudaStreamDestroy(c->stream); }
   delete c; *pc = nullptr;
   return XSB_OK;
@@ -215,7 +219,7 @@ int xsb_mat_mult_dev(xsb_ctx c, int which, const double *x, double *y)
 {
   NEED_DEVICE(c);
   const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
-  if (S) return spmv_csr(c, *S, x, y);
+  if (S) return which == XSB_MAT_A ? op_full_mult(c, x, y) : spmv_csr(c, *S, x, y);
   Epilogue ep;
   if (which == XSB_MAT_A00_MF) { XSB_CHK(mf_setup(c)); return mf_a00_apply(c, x, y, ep); }
   return spmv_baij(c, *B, x, y, ep);
@@ -385,6 +389,24 @@ int xsb_ksp_get_counters(xsb_ctx c, int64_t out[8])
   for (int i = 0; i < 4; ++i) out[4 + i] = c->a00_mode[i];
   return XSB_OK;
 }
+int xsb_comm_unique_id(void *out128) { return comm_unique_id(out128); }
+int xsb_comm_init(xsb_ctx c, const void *unique_id, int rank, int nranks)
+{
+  NEED_DEVICE(c);
+  if (c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_comm_init must precede xsb_assemble");
+  return comm_init(c, unique_id, rank, nranks);
+}
+int xsb_get_partition(xsb_ctx c, int64_t out[12])
+{
+  if (!c || !out) return XSB_ERR_ARG;
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_get_partition before xsb_assemble");
+  const Slab &S = c->slab; const Lattice &L = c->lat;
+  out[0] = S.rank; out[1] = S.nranks; out[2] = S.k0; out[3] = S.k1; out[4] = S.e0; out[5] = S.e1;
+  out[6] = c->own_u.off0; out[7] = c->own_u.len0; out[8] = L.nu + c->own_p.off0; out[9] = c->own_p.len0;
+  out[10] = (int64_t)(2 * S.k0) * L.NX * L.NY * L.nsd;   /* global index of the first owned velocity dof */
+  out[11] = (int64_t)S.k0 * L.PX * L.PY;                 /* global index of the first owned pressure dof */
+  return XSB_OK;
+}
 int xsb_get_stream(xsb_ctx c, void **stream) { if (!c || !stream) return XSB_ERR_ARG; *stream = (void *)c->stream; return XSB_OK; }
 
 int xsb_diagnostics(xsb_ctx c, const double *x, double *out)
@@ -445,6 +467,14 @@ int64_t xsb_prealloc_total(int nsd, int mx, int my, int mz)
 
 int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int mz, int32_t *idx, double *val, int cap)
 {
+  return bc_list_faces(nsd, lame, model, freeslip, mx, my, mz, 1, 1, idx, val, cap);
+}
+
+}   // extern "C"
+
+// Dirichlet list of a (local) lattice; zlo/zhi say whether its z = 0 / z = max planes are physical boundary faces
+int bc_list_faces(int nsd, int lame, int model, int freeslip, int mx, int my, int mz, int zlo, int zhi, int32_t *idx, double *val, int cap)
+{
   Lattice L; make_lattice(nsd, mx, my, mz, L);
   const int ni = L.NX, nj = L.NY, nk = L.NZ, N = L.NY, M = L.NX;
   int type = BC_SOLCX;
@@ -466,10 +496,10 @@ int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int 
     } else {
       for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(0, j, k, 0, 0.0);
       for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, 0, k, 1, 0.0);
-      for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, 0, 2, 0.0);
+      if (zlo) for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, 0, 2, 0.0);
       for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(ni - 1, j, k, 0, 0.0);
       if (freeslip) for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, nj - 1, k, 1, 0.0);
-      for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, nk - 1, 2, 0.0);
+      if (zhi) for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, nk - 1, 2, 0.0);
     }
     break;
   case BC_FIXEDBASE:   // models.c:197-225
@@ -483,8 +513,8 @@ int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int 
     for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(0, j, k, 0, 0.1);
     if (ni == N) for (int j = 0; j < nj; ++j) for (int k = 0; k < nk; ++k) push(ni - 1, j, k, 0, -0.1);
     for (int i = 0; i < ni; ++i) for (int k = 0; k < nk; ++k) push(i, 0, k, 1, 0.0);
-    for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, 0, 2, 0.0);
-    for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, nk - 1, 2, 0.0);
+    if (zlo) for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, 0, 2, 0.0);
+    if (zhi) for (int i = 0; i < ni; ++i) for (int j = 0; j < nj; ++j) push(i, j, nk - 1, 2, 0.0);
     break;
   case BC_MMS1:   // models.c:505-593; values are filled from the coordinates by the caller
     for (int j = 0; j < nj; ++j) for (int d = 0; d < 2; ++d) push(0, j, 0, d, 0.0);
@@ -495,6 +525,8 @@ int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int 
   }
   return cnt;
 }
+
+extern "C" {
 
 int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, int dims[3])
 {
@@ -508,6 +540,21 @@ int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, in
       if (n[d] < 2) return XSB_ERR_ARG;
     }
   dims[0] = n[0]; dims[1] = n[1]; dims[2] = n[2];
+  return XSB_OK;
+}
+
+int xsb_slab_layout(int nsd, int mx, int my, int mz, int nranks, int rank, int64_t out[12])
+{
+  if (nsd != 3 || !out) return XSB_ERR_ARG;
+  int k0, k1; if (xsb_slab_range(mz, nranks, rank, &k0, &k1)) return XSB_ERR_ARG;
+  const int e0 = nranks > 1 ? (k0 - 2 < 0 ? 0 : k0 - 2) : 0, e1 = nranks > 1 ? (k1 + 1 > mz ? mz : k1 + 1) : mz;
+  const bool last = rank == nranks - 1;
+  const int64_t NX = 2 * mx + 1, NY = 2 * my + 1, PX = mx + 1, PY = my + 1, nzl = 2 * (e1 - e0) + 1;
+  const int64_t pu = 3 * NX * NY, pp = PX * PY, nu_loc = pu * nzl;
+  const int ou0 = 2 * (k0 - e0), ou1 = 2 * (k1 - e0) + (last ? 1 : 0), op0 = k0 - e0, op1 = k1 - e0 + (last ? 1 : 0);
+  out[0] = rank; out[1] = nranks; out[2] = k0; out[3] = k1; out[4] = e0; out[5] = e1;
+  out[6] = ou0 * pu; out[7] = (ou1 - ou0) * pu; out[8] = nu_loc + op0 * pp; out[9] = (op1 - op0) * pp;
+  out[10] = (int64_t)(2 * k0) * pu; out[11] = (int64_t)k0 * pp;
   return XSB_OK;
 }
 

@@ -76,6 +76,25 @@ int fe_resolve_model(xsb_ctx c)
   L.nun = (int64_t)L.NX * L.NY * L.NZ; L.npn = (int64_t)L.PX * L.PY * L.PZ;
   L.nu = nsd * L.nun; L.np = L.npn; L.n = L.nu + L.np; L.nel = (int64_t)L.mx * L.my * L.mz;
   L.hu[0] = size[0] / (L.NX - 1); L.hu[1] = size[1] / (L.NY - 1); L.hu[2] = nsd == 3 ? size[2] / (L.NZ - 1) : 1.0;
+  {   // z-slab partition: shrink the lattice to this rank's local element layers (coordinates stay global)
+    Slab &S = c->slab; const int mzg = L.mz;
+    S.mz_glob = mzg; S.k0 = 0; S.k1 = mzg; S.e0 = 0; S.e1 = mzg;
+    if (S.nranks > 1) {
+      if (xsb_slab_range(mzg, S.nranks, S.rank, &S.k0, &S.k1)) return xsb_fail(c, XSB_ERR_ARG, "-mz %d cannot be cut into %d slabs", mzg, S.nranks);
+      S.e0 = S.k0 - 2 < 0 ? 0 : S.k0 - 2; S.e1 = S.k1 + 1 > mzg ? mzg : S.k1 + 1;
+    }
+    const bool last = S.rank == S.nranks - 1;
+    L.mz = S.e1 - S.e0; L.zoff = S.e0;
+    L.NZ = nsd == 3 ? 2 * L.mz + 1 : 1; L.PZ = nsd == 3 ? L.mz + 1 : 1;
+    L.nun = (int64_t)L.NX * L.NY * L.NZ; L.npn = (int64_t)L.PX * L.PY * L.PZ;
+    L.nu = nsd * L.nun; L.np = L.npn; L.n = L.nu + L.np; L.nel = (int64_t)L.mx * L.my * L.mz;
+    S.ou0 = nsd == 3 ? 2 * (S.k0 - S.e0) : 0; S.ou1 = nsd == 3 ? 2 * (S.k1 - S.e0) + (last ? 1 : 0) : 1;
+    S.op0 = nsd == 3 ? S.k0 - S.e0 : 0;       S.op1 = nsd == 3 ? S.k1 - S.e0 + (last ? 1 : 0) : 1;
+    const int64_t pu = (int64_t)nsd * L.NX * L.NY, pp = (int64_t)L.PX * L.PY;
+    c->own_u = Ranges(); c->own_u.off0 = S.ou0 * pu; c->own_u.len0 = (S.ou1 - S.ou0) * pu;
+    c->own_p = Ranges(); c->own_p.off0 = S.op0 * pp; c->own_p.len0 = (S.op1 - S.op0) * pp;
+    c->own_full = c->own_u; c->own_full.off1 = L.nu + c->own_p.off0; c->own_full.len1 = c->own_p.len0;
+  }
   if (L.n >= INT32_MAX) return xsb_fail(c, XSB_ERR_SUP, "more than 2^31 unknowns: the assembled AIJ path uses 32-bit PetscInt indices");
   m.model = o.integer("model", c->lame ? 6 : 2);   // models.h:9-13
   m.freeslip = o.flag("freesliphack");
@@ -229,7 +248,7 @@ __global__ void coeff_eval_kernel(Lattice L, Model m, int lame, const FeTables *
     int ii = i % 3, jj = (i / 3) % 3, kk = i / 9;
     double N = T->Nu[q][i];
     xq[0] += N * (L.hu[0] * (2 * ei + ii)); xq[1] += N * (L.hu[1] * (2 * ej + jj));
-    if (L.nsd == 3) xq[2] += N * (L.hu[2] * (2 * ek + kk));
+    if (L.nsd == 3) xq[2] += N * (L.hu[2] * (2 * (ek + L.zoff) + kk));
   }
   double out[XSB_NSLOT];
   eval_model(m, lame, L.nsd, xq, out);
@@ -601,9 +620,10 @@ int fe_assemble(xsb_ctx c)
   }
   // Dirichlet data: index list built on the host (integer logic of ISCreate_BCList), applied on the device
   {
-    int cap = xsb_bc_list(nsd, c->lame, c->mdl.model, c->mdl.freeslip, L.mx, L.my, L.mz, nullptr, nullptr, 0);
+    const int zlo = c->slab.e0 == 0, zhi = c->slab.e1 == c->slab.mz_glob;   // which z faces of the local lattice are physical boundaries
+    int cap = bc_list_faces(nsd, c->lame, c->mdl.model, c->mdl.freeslip, L.mx, L.my, L.mz, zlo, zhi, nullptr, nullptr, 0);
     std::vector<int32_t> idx(cap > 0 ? cap : 1); std::vector<double> val(cap > 0 ? cap : 1);
-    c->nbc = xsb_bc_list(nsd, c->lame, c->mdl.model, c->mdl.freeslip, L.mx, L.my, L.mz, idx.data(), val.data(), cap);
+    c->nbc = bc_list_faces(nsd, c->lame, c->mdl.model, c->mdl.freeslip, L.mx, L.my, L.mz, zlo, zhi, idx.data(), val.data(), cap);
     if (c->mdl.bc_type == BC_MMS1) {   // values from the coordinates (models.c:505-593)
       for (int t = 0; t < c->nbc; ++t) {
         int64_t nd = idx[t] / 2; int d = idx[t] % 2; double x = L.hu[0] * (nd % L.NX), y = L.hu[1] * (nd / L.NX);

@@ -186,14 +186,57 @@ k_ilu0_solve(int nw, int np, const int *__restrict__ off, const int *__restrict_
   }
 }
 
+// bjacobi block of this rank: rows and columns of the owned pressure planes [op0,op1) of the local lattice, as a
+// 27-point matrix on the owned sub-lattice (PETSc PCBJACOBI: the rank's diagonal block of Mpscaled).
+__global__ void k_own_len(PLat P, int *len)
+{
+  int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= P.px * P.py * P.pz) return;
+  const BoxPattern pat{P.px, P.py, P.pz, 0};
+  len[row] = box_size(pat, row % P.px, (row / P.px) % P.py, row / (P.px * P.py));
+}
+__global__ void k_own_fill(PLat P, int op0, int pz_loc, const int *__restrict__ sia, const double *__restrict__ sa, const int *__restrict__ dia, int *dja, double *da)
+{
+  int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= P.px * P.py * P.pz) return;
+  const int i = row % P.px, j = (row / P.px) % P.py, k = row / (P.px * P.py), ks = k + op0;
+  int l0, h0, l1, h1, l2, h2, s2, t2;
+  range_pp(i, P.px, l0, h0); range_pp(j, P.py, l1, h1); range_pp(k, P.pz, l2, h2); range_pp(ks, pz_loc, s2, t2);
+  const int nx = h0 - l0 + 1, ny = h1 - l1 + 1, srow = i + j * P.px + ks * P.px * P.py;
+  int d = dia[row];
+  for (int kk = l2; kk <= h2; ++kk) for (int jj = l1; jj <= h1; ++jj) for (int ii = l0; ii <= h0; ++ii) {
+    dja[d] = ii + jj * P.px + kk * P.px * P.py;
+    da[d] = sa[sia[srow] + ((kk + op0 - s2) * ny + (jj - l1)) * nx + (ii - l0)];
+    ++d;
+  }
+}
+static int build_owned_block(xsb_ctx c, Csr &B)
+{
+  const Lattice &L = c->lat; const Slab &S = c->slab; cudaStream_t st = c->stream;
+  PLat P{L.PX, L.PY, S.op1 - S.op0}; const int np = P.px * P.py * P.pz;
+  int *len = nullptr; XSB_CHK(dev_alloc(c, &len, (size_t)np + 1)); XSB_CHK(dev_alloc(c, &B.ia, (size_t)np + 1));
+  k_own_len<<<(np + 255) / 256, 256, 0, st>>>(P, len); KERNEL_OK();
+  void *tmp = nullptr; size_t tb = 0;
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, B.ia, np + 1, st));
+  CUDA_OK(cudaMalloc(&tmp, tb));
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, len, B.ia, np + 1, st));
+  int tot = 0; CUDA_OK(cudaMemcpyAsync(&tot, B.ia + np, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(tmp));
+  B.n = B.m = np; B.nnz = tot;
+  XSB_CHK(dev_alloc(c, &B.ja, (size_t)tot)); XSB_CHK(dev_alloc(c, &B.a, (size_t)tot));
+  k_own_fill<<<(np + 255) / 256, 256, 0, st>>>(P, S.op0, L.PZ, c->Mp.ia, c->Mp.a, B.ia, B.ja, B.a); KERNEL_OK();
+  return 0;
+}
+
 int ilu_setup(xsb_ctx c)
 {
-  const Lattice &L = c->lat; PLat P{L.PX, L.PY, L.PZ}; cudaStream_t st = c->stream;
-  const int np = (int)L.npn, nw = (P.px - 1) + 2 * (P.py - 1) + 4 * (P.pz - 1) + 1;
-  XSB_CHK(dev_alloc(c, &c->mp_lu, (size_t)c->Mp.nnz));
+  const Lattice &L = c->lat; cudaStream_t st = c->stream;
+  if (c->slab.nranks > 1) XSB_CHK(build_owned_block(c, c->MpOwn)); else c->MpOwn = c->Mp;
+  const Csr &M = c->MpOwn;
+  PLat P{L.PX, L.PY, c->slab.op1 - c->slab.op0};
+  const int np = P.px * P.py * P.pz, nw = (P.px - 1) + 2 * (P.py - 1) + 4 * (P.pz - 1) + 1;
+  XSB_CHK(dev_alloc(c, &c->mp_lu, (size_t)M.nnz));
   int *flag = nullptr; XSB_CHK(dev_alloc(c, &flag, 1));
   CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  k_ilu0_factor<<<1, 1024, 0, st>>>(P, c->Mp.ia, c->Mp.a, c->mp_lu, flag); KERNEL_OK();
+  k_ilu0_factor<<<1, 1024, 0, st>>>(P, M.ia, M.a, c->mp_lu, flag); KERNEL_OK();
   // level schedule
   int *cnt = nullptr, *cursor = nullptr, *diag = nullptr;
   XSB_CHK(dev_alloc(c, &cnt, (size_t)nw + 1)); XSB_CHK(dev_alloc(c, &cursor, (size_t)nw + 1));
@@ -205,7 +248,7 @@ int ilu_setup(xsb_ctx c)
     CUDA_OK(cudaMalloc(&tmp, tb));
     CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, c->ilu_lvl_off, nw + 1, st));
     CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(tmp)); }
-  k_lvl_fill<<<(np + 255) / 256, 256, 0, st>>>(P, c->ilu_lvl_off, cursor, c->ilu_rows, diag, c->Mp.ia); KERNEL_OK();
+  k_lvl_fill<<<(np + 255) / 256, 256, 0, st>>>(P, c->ilu_lvl_off, cursor, c->ilu_rows, diag, M.ia); KERNEL_OK();
   c->ilu_nlvl = nw; c->ilu_diag = diag;
   {
     int *lvl_of_q = nullptr; XSB_CHK(dev_alloc(c, &lvl_of_q, (size_t)np));
@@ -213,7 +256,7 @@ int ilu_setup(xsb_ctx c)
     XSB_CHK(dev_alloc(c, &c->ilu_bcol, (size_t)13 * np + 64)); XSB_CHK(dev_alloc(c, &c->ilu_bval, (size_t)13 * np + 64)); XSB_CHK(dev_alloc(c, &c->ilu_bn, (size_t)np));
     XSB_CHK(dev_alloc(c, &c->ilu_binv, (size_t)np));
     k_lvl_of_q<<<nw, 256, 0, st>>>(nw, c->ilu_lvl_off, lvl_of_q); KERNEL_OK();
-    k_ilu_pack<<<(np + 255) / 256, 256, 0, st>>>(nw, c->ilu_lvl_off, c->ilu_rows, c->Mp.ia, c->Mp.ja, diag, c->mp_lu, lvl_of_q,
+    k_ilu_pack<<<(np + 255) / 256, 256, 0, st>>>(nw, c->ilu_lvl_off, c->ilu_rows, M.ia, M.ja, diag, c->mp_lu, lvl_of_q,
                                                    c->ilu_fcol, c->ilu_fval, c->ilu_fn, c->ilu_bcol, c->ilu_bval, c->ilu_bn, c->ilu_binv); KERNEL_OK();
   }
   int h = 0; CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
@@ -223,7 +266,7 @@ int ilu_setup(xsb_ctx c)
 
 int ilu_apply(xsb_ctx c, const double *b, double *x)
 {
-  k_ilu0_solve<<<ILU_CLUSTER, ILU_TPB, sizeof(int) * (c->ilu_nlvl + 1), c->stream>>>(c->ilu_nlvl, (int)c->lat.npn, c->ilu_lvl_off, c->ilu_rows, c->ilu_fcol, c->ilu_fval, c->ilu_fn,
+  k_ilu0_solve<<<ILU_CLUSTER, ILU_TPB, sizeof(int) * (c->ilu_nlvl + 1), c->stream>>>(c->ilu_nlvl, c->MpOwn.n, c->ilu_lvl_off, c->ilu_rows, c->ilu_fcol, c->ilu_fval, c->ilu_fn,
                                                        c->ilu_bcol, c->ilu_bval, c->ilu_bn, c->ilu_binv, b, x); KERNEL_OK();
   return 0;
 }

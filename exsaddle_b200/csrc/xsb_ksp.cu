@@ -55,7 +55,15 @@ int hess_eig(int n, const double *H, int ldh, double *wr, double *wi)
 }
 
 // ------------------------------------------------------------------ operators
-static int full_mult(xsb_ctx c, const double *x, double *y) { c->n_a++; return spmv_csr(c, c->A, x, y); }
+// y = A x on the full saddle operator; on slabs: ghost update of x, then the owned velocity and pressure rows
+int op_full_mult(xsb_ctx c, const double *x, double *y)
+{
+  if (c->slab.nranks == 1) return spmv_csr(c, c->A, x, y);
+  XSB_CHK(comm_halo_full(c, const_cast<double *>(x)));
+  XSB_CHK(spmv_csr(c, c->A, x, y, c->own_full.off0, c->own_full.len0));
+  return spmv_csr(c, c->A, x, y, c->own_full.off1, c->own_full.len1);
+}
+static int full_mult(xsb_ctx c, const double *x, double *y) { c->n_a++; return op_full_mult(c, x, y); }
 static int a00_mult(xsb_ctx c, const double *x, double *y) { Epilogue ep; return spmv_a00_fine(c, c->A00, x, y, ep); }
 
 // ------------------------------------------------------------------ KSPSolve_GCR on A00, right PC = PCMG
@@ -67,7 +75,8 @@ static int gcr_solve(xsb_ctx c, const double *b, double *x, int *its_out)
   int its = 0; bool done = false;
   XSB_CHK(vec_set(c, n, 0.0, x));
   XSB_CHK(vec_copy(c, n, b, r));            // r = b - A*0
-  XSB_CHK(vec_mdot(c, n, r, nullptr, 0, true, dots + 66));
+  const Ranges &rg = c->own_u;
+  XSB_CHK(vec_mdot(c, rg, r, nullptr, 0, true, dots + 66));
   XSB_CHK(vec_fetch(c, dots + 66, 1, h));
   const double rnorm0 = sqrt(h[0]), ttol = fmax(s.u_rtol * rnorm0, 1e-50);
   if (rnorm0 <= ttol) { *its_out = 0; return 0; }
@@ -78,12 +87,12 @@ static int gcr_solve(xsb_ctx c, const double *b, double *x, int *its_out)
       XSB_CHK(mg_vcycle(c, r, sv));                                   // s = B^-1 r
       XSB_CHK(a00_mult(c, sv, v));                                    // v = A s
       if (k > 0) {
-        XSB_CHK(vec_mdot(c, n, v, c->GV.data(), k, false, dots));     // VecMDot
+        XSB_CHK(vec_mdot(c, rg, v, c->GV.data(), k, false, dots));    // VecMDot
         XSB_CHK(vec_maxpy_dev(c, n, v, c->GV.data(), k, dots, -1.0)); // v -= sum (v.v_i) v_i
         XSB_CHK(vec_maxpy_dev(c, n, sv, c->GS.data(), k, dots, -1.0));
       }
-      { double *two[2] = {r, v}; XSB_CHK(vec_mdot(c, n, v, two, 2, false, dots + 64)); }   // VecDotNorm2: [r.v, v.v]
-      XSB_CHK(vec_gcr_update(c, n, dots + 64, v, sv, x, r, dots + 66));
+      { double *two[2] = {r, v}; XSB_CHK(vec_mdot(c, rg, v, two, 2, false, dots + 64)); }   // VecDotNorm2: [r.v, v.v]
+      XSB_CHK(vec_gcr_update(c, rg, dots + 64, v, sv, x, r, dots + 66));
       XSB_CHK(vec_fetch(c, dots + 66, 1, h));
       const double norm_r = sqrt(h[0]);
       its++;
@@ -103,8 +112,9 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner)
   if (c->so.pc_type == 0) return vec_copy(c, L.n, r, z);
   // PCApply_FieldSplit_Schur, PC_FIELDSPLIT_SCHUR_FACT_UPPER
   double *yp = z + L.nu;
-  if (c->so.p_pc == 0) XSB_CHK(ilu_apply(c, r + L.nu, yp)); else XSB_CHK(vec_pmult(c, L.np, c->mp_idiag, r + L.nu, yp));
-  XSB_CHK(spmv_csr(c, c->A01, yp, c->fs_tu));
+  if (c->so.p_pc == 0) XSB_CHK(ilu_apply(c, r + L.nu + c->own_p.off0, yp + c->own_p.off0)); else XSB_CHK(vec_pmult(c, L.np, c->mp_idiag, r + L.nu, yp));
+  XSB_CHK(comm_halo_p(c, yp));
+  XSB_CHK(spmv_csr(c, c->A01, yp, c->fs_tu, c->own_u.off0, c->own_u.len0));
   XSB_CHK(vec_aypx(c, L.nu, -1.0, r, c->fs_tu));      // t_u = x_u - A01 y_p
   int its = 0;
   XSB_CHK(gcr_solve(c, c->fs_tu, z, &its));
@@ -218,7 +228,7 @@ int ksp_solve(xsb_ctx c, const double *b, double *x)
     else { XSB_CHK(full_mult(c, x, t1)); XSB_CHK(vec_aypx(c, n, -1.0, b, t1)); }
     first = false;
     if (!flex && !right && haspc) XSB_CHK(pc_apply(c, t1, c->V[0], nullptr)); else XSB_CHK(vec_copy(c, n, t1, c->V[0]));
-    XSB_CHK(vec_mdot(c, n, c->V[0], nullptr, 0, true, c->scal));
+    XSB_CHK(vec_mdot(c, c->own_full, c->V[0], nullptr, 0, true, c->scal));
     XSB_CHK(vec_fetch(c, c->scal, 1, hcol.data()));
     res = sqrt(hcol[0]);
     if (c->its == 0) { rnorm0 = res; ttol = fmax(s.rtol * rnorm0, s.atol); }
@@ -243,9 +253,9 @@ int ksp_solve(xsb_ctx c, const double *b, double *x)
         if (haspc) { XSB_CHK(full_mult(c, c->V[it], t2)); XSB_CHK(pc_apply(c, t2, w, nullptr)); } else XSB_CHK(full_mult(c, c->V[it], w));
       }
       // classical Gram-Schmidt: h = V^T w ; w -= V h ; ||w||   (coefficients never leave the device)
-      XSB_CHK(vec_mdot(c, n, w, c->V.data(), it + 1, false, c->scal));
+      XSB_CHK(vec_mdot(c, c->own_full, w, c->V.data(), it + 1, false, c->scal));
       XSB_CHK(vec_maxpy_dev(c, n, w, c->V.data(), it + 1, c->scal, -1.0));
-      XSB_CHK(vec_mdot(c, n, w, nullptr, 0, true, c->scal + it + 1));
+      XSB_CHK(vec_mdot(c, c->own_full, w, nullptr, 0, true, c->scal + it + 1));
       XSB_CHK(vec_scale_by_inv_sqrt(c, n, w, c->scal + it + 1));
       XSB_CHK(vec_fetch(c, c->scal, it + 2, hcol.data()));
       hcol[it + 1] = sqrt(hcol[it + 1]);

@@ -15,32 +15,35 @@
 static inline unsigned nblk(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
 // ------------------------------------------------------------------ K8: transfers
-// bc = P^T rf : one thread per coarse node, fine contributions gathered in ascending fine index (MatRestrict)
+// The fine vector lives on a (possibly slab-local) lattice whose plane 0 is global plane fz0; the coarse vector is
+// always indexed globally.  bc = P^T rf for the coarse planes [K0,K1): one thread per coarse node, fine
+// contributions gathered in ascending fine index (MatRestrict).
 template <int BS>
-__global__ void k_restrict(int fnx, int fny, int fnz, int cnx, int cny, int cnz, const double *__restrict__ rf, double *__restrict__ bc)
+__global__ void k_restrict(int fnx, int fny, int fnz, int fz0, int cnx, int cny, int K0, int K1, const double *__restrict__ rf, double *__restrict__ bc)
 {
-  int64_t cn = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (cn >= (int64_t)cnx * cny * cnz) return;
-  const int I = (int)(cn % cnx), J = (int)((cn / cnx) % cny), K = (int)(cn / ((int64_t)cnx * cny));
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (t >= (int64_t)cnx * cny * (K1 - K0)) return;
+  const int I = (int)(t % cnx), J = (int)((t / cnx) % cny), K = K0 + (int)(t / ((int64_t)cnx * cny));
   double acc[BS];
 #pragma unroll
   for (int d = 0; d < BS; ++d) acc[d] = 0.0;
   for (int c = -1; c <= 1; ++c) for (int b = -1; b <= 1; ++b) for (int a = -1; a <= 1; ++a) {
-    const int i = 2 * I + a, j = 2 * J + b, k = 2 * K + c;
+    const int i = 2 * I + a, j = 2 * J + b, k = 2 * K + c - fz0;
     if (i < 0 || i >= fnx || j < 0 || j >= fny || k < 0 || k >= fnz) continue;
     const double w = (a ? 0.5 : 1.0) * (b ? 0.5 : 1.0) * (c ? 0.5 : 1.0);
     const int64_t f = i + (int64_t)j * fnx + (int64_t)k * fnx * fny;
 #pragma unroll
     for (int d = 0; d < BS; ++d) acc[d] += w * rf[BS * f + d];
   }
+  const int64_t cn = I + (int64_t)J * cnx + (int64_t)K * cnx * cny;
 #pragma unroll
   for (int d = 0; d < BS; ++d) bc[BS * cn + d] = acc[d];
 }
-// xf += P xc : one thread per fine node (MatInterpolateAdd)
+// xf += P xc for the fine planes [z0,z1) (local indices): one thread per fine node (MatInterpolateAdd)
 template <int BS>
-__global__ void k_prolong_add(int fnx, int fny, int fnz, int cnx, int cny, const double *__restrict__ xc, double *__restrict__ xf)
+__global__ void k_prolong_add(int fnx, int fny, int z0, int z1, int fz0, int cnx, int cny, const double *__restrict__ xc, double *__restrict__ xf)
 {
-  int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (f >= (int64_t)fnx * fny * fnz) return;
-  const int i = (int)(f % fnx), j = (int)((f / fnx) % fny), k = (int)(f / ((int64_t)fnx * fny));
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (t >= (int64_t)fnx * fny * (z1 - z0)) return;
+  const int i = (int)(t % fnx), j = (int)((t / fnx) % fny), kl = z0 + (int)(t / ((int64_t)fnx * fny)), k = kl + fz0;
   const int i0 = i >> 1, j0 = j >> 1, k0 = k >> 1, ni = 1 + (i & 1), nj = 1 + (j & 1), nk = 1 + (k & 1);
   const double w = (ni == 2 ? 0.5 : 1.0) * (nj == 2 ? 0.5 : 1.0) * (nk == 2 ? 0.5 : 1.0);
   double acc[BS];
@@ -51,21 +54,32 @@ __global__ void k_prolong_add(int fnx, int fny, int fnz, int cnx, int cny, const
 #pragma unroll
     for (int d = 0; d < BS; ++d) acc[d] += w * xc[BS * cn + d];
   }
+  const int64_t f = i + (int64_t)j * fnx + (int64_t)kl * fnx * fny;
 #pragma unroll
   for (int d = 0; d < BS; ++d) xf[BS * f + d] += acc[d];
 }
 int mg_restrict(xsb_ctx c, const Level &F, const Level &C, const double *rf, double *bc)
 {
-  const int64_t nc = (int64_t)C.nx * C.ny * C.nz;
-  if (c->nsd == 3) k_restrict<3><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, C.nz, rf, bc);
-  else k_restrict<2><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, C.nz, rf, bc);
-  KERNEL_OK(); return 0;
+  const Slab &S = c->slab;
+  int fz0 = 0, K0 = 0, K1 = C.nz;
+  if (F.dist) {   // owned coarse planes only; the ghost plane below is refreshed first, the result is replicated after
+    XSB_CHK(comm_halo_u(c, const_cast<double *>(rf)));
+    fz0 = 2 * S.e0; K0 = S.k0; K1 = S.rank == S.nranks - 1 ? C.nz : S.k1;
+  }
+  const int64_t nc = (int64_t)C.nx * C.ny * (K1 - K0);
+  if (c->nsd == 3) k_restrict<3><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, fz0, C.nx, C.ny, K0, K1, rf, bc);
+  else k_restrict<2><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, fz0, C.nx, C.ny, K0, K1, rf, bc);
+  KERNEL_OK();
+  if (F.dist) XSB_CHK(comm_bcast_planes(c, bc, (int64_t)c->nsd * C.nx * C.ny, C.nz));
+  return 0;
 }
 int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, double *xf)
 {
-  const int64_t nf = (int64_t)F.nx * F.ny * F.nz;
-  if (c->nsd == 3) k_prolong_add<3><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, xc, xf);
-  else k_prolong_add<2><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, F.nz, C.nx, C.ny, xc, xf);
+  const Slab &S = c->slab;
+  const int z0 = F.dist ? S.ou0 : 0, z1 = F.dist ? S.ou1 : F.nz, fz0 = F.dist ? 2 * S.e0 : 0;
+  const int64_t nf = (int64_t)F.nx * F.ny * (z1 - z0);
+  if (c->nsd == 3) k_prolong_add<3><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, z0, z1, fz0, C.nx, C.ny, xc, xf);
+  else k_prolong_add<2><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, z0, z1, fz0, C.nx, C.ny, xc, xf);
   KERNEL_OK(); return 0;
 }
 
@@ -141,6 +155,56 @@ static int galerkin(xsb_ctx c, const Level &F, Level &C)
   if (bs == 3) k_galerkin<3><<<nblk(ncn * 27, 128), 128, 0, st>>>(F.A.pat, F.A.ia, F.A.a, cp, A.ia, A.ja, A.a);
   else k_galerkin<2><<<nblk(ncn * 27, 128), 128, 0, st>>>(F.A.pat, F.A.ia, F.A.a, cp, A.ia, A.ja, A.a);
   KERNEL_OK();
+  CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(len));
+  C.owns_A = true;
+  return 0;
+}
+
+// box-pattern block columns of a lattice matrix
+__global__ void k_box_ja(BoxPattern p, const int *__restrict__ ia, int *__restrict__ ja)
+{
+  int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (nd >= (int64_t)p.nx * p.ny * p.nz) return;
+  const int i = (int)(nd % p.nx), j = (int)((nd / p.nx) % p.ny), k = (int)(nd / ((int64_t)p.nx * p.ny));
+  int l0, h0, l1, h1, l2, h2; box_range(p, i, p.nx, l0, h0); box_range(p, j, p.ny, l1, h1); box_range(p, k, p.nz, l2, h2);
+  int cpos = ia[nd];
+  for (int kk = l2; kk <= h2; ++kk) for (int jj = l1; jj <= h1; ++jj) for (int ii = l0; ii <= h0; ++ii) ja[cpos++] = ii + jj * p.nx + kk * p.nx * p.ny;
+}
+
+// Slab-partitioned fine level -> replicated first coarse level.  Every rank forms P^T A P on its local lattice (the
+// rows of its owned coarse planes are complete: SURVEY 8e / Slab comment), copies them into the global box-pattern
+// matrix and all ranks exchange their row ranges (ncclBroadcast per rank; set-up only).
+static int galerkin_replicate(xsb_ctx c, const Level &F, Level &C)
+{
+  const int bs = c->nsd, bs2 = bs * bs; cudaStream_t st = c->stream; const Slab &S = c->slab;
+  Level T; T.nx = (F.nx - 1) / 2 + 1; T.ny = (F.ny - 1) / 2 + 1; T.nz = (F.nz - 1) / 2 + 1;
+  XSB_CHK(galerkin(c, F, T));
+  BoxPattern gp{C.nx, C.ny, C.nz, 0};
+  const int64_t ncn = (int64_t)C.nx * C.ny * C.nz, pn = (int64_t)C.nx * C.ny;
+  int64_t *len = nullptr; CUDA_OK(cudaMalloc(&len, sizeof(int64_t) * (ncn + 1)));
+  k_box_len<<<nblk(ncn), 256, 0, st>>>(gp, len); KERNEL_OK();
+  CUDA_OK(cudaMemsetAsync(len + ncn, 0, sizeof(int64_t), st));
+  void *tmp = nullptr; size_t tb = 0;
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, len, ncn + 1, st));
+  CUDA_OK(cudaMalloc(&tmp, tb));
+  CUDA_OK(cub::DeviceScan::ExclusiveSum(tmp, tb, len, len, ncn + 1, st));
+  std::vector<int64_t> gia(ncn + 1);
+  CUDA_OK(cudaMemcpyAsync(gia.data(), len, sizeof(int64_t) * (ncn + 1), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(tmp));
+  Baij &A = C.A; A.nb = (int)ncn; A.bs = bs; A.nblk = gia[ncn]; A.pat = gp;
+  XSB_CHK(dev_alloc(c, &A.ia, (size_t)ncn + 1)); XSB_CHK(dev_alloc(c, &A.ja, (size_t)A.nblk)); XSB_CHK(dev_alloc(c, &A.a, (size_t)A.nblk * bs2 + 2));
+  k_narrow<<<nblk(ncn + 1), 256, 0, st>>>(ncn, len, A.ia); KERNEL_OK();
+  k_box_ja<<<nblk(ncn), 256, 0, st>>>(gp, A.ia, A.ja); KERNEL_OK();
+  // my rows: global coarse planes [K0,K1) = local planes [K0-e0, K1-e0) of T (identical boxes, see above)
+  const int K0 = S.k0, K1 = S.rank == S.nranks - 1 ? C.nz : S.k1;
+  std::vector<int> tia(T.A.nb + 1);
+  CUDA_OK(cudaMemcpy(tia.data(), T.A.ia, sizeof(int) * (T.A.nb + 1), cudaMemcpyDeviceToHost));
+  const int64_t g0 = gia[K0 * pn], g1 = gia[K1 * pn], l0 = tia[(K0 - S.e0) * pn], l1 = tia[(K1 - S.e0) * pn];
+  if (g1 - g0 != l1 - l0) return xsb_fail(c, XSB_ERR_ARG, "slab Galerkin: local and global row ranges differ (%lld vs %lld blocks)", (long long)(l1 - l0), (long long)(g1 - g0));
+  CUDA_OK(cudaMemcpyAsync(A.a + g0 * bs2, T.A.a + l0 * bs2, sizeof(double) * (g1 - g0) * bs2, cudaMemcpyDeviceToDevice, st));
+  std::vector<int64_t> offs(S.nranks + 1);
+  for (int r = 0; r < S.nranks; ++r) { int a0, a1; xsb_slab_range(S.mz_glob, S.nranks, r, &a0, &a1); offs[r] = gia[a0 * pn] * bs2; }
+  offs[S.nranks] = gia[ncn] * bs2;
+  XSB_CHK(comm_bcast_segments(c, A.a, offs.data()));
   CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(len));
   C.owns_A = true;
   return 0;
@@ -261,6 +325,15 @@ static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, doubl
 {
   return fine ? spmv_a00_fine(c, L.A, x, y, ep) : spmv_baij(c, L.A, x, y, ep);
 }
+// set-up products (eigenvalue estimate): not counted; slab levels refresh ghosts and compute owned rows only
+static int level_spmv(xsb_ctx c, const Level &L, const double *x, double *y)
+{
+  Epilogue ep;
+  if (!L.dist) return spmv_baij(c, L.A, x, y, ep);
+  XSB_CHK(comm_halo_u(c, const_cast<double *>(x)));
+  const int pn = L.nx * L.ny;
+  return spmv_baij(c, L.A, x, y, ep, c->slab.ou0 * pn, (c->slab.ou1 - c->slab.ou0) * pn);
+}
 
 // KSPSolve_Chebyshev, Jacobi PC, nonzero initial guess, norm none: first correction + (its-1) recurrence steps.
 // Result ends in L.x (buffers are rotated by pointer swap, no copies).
@@ -331,9 +404,11 @@ static int cheb_estimate(xsb_ctx c, Level &L)
   for (auto &v : V) XSB_CHK(dev_alloc(c, &v, (size_t)n));
   double *t = L.r;
   std::vector<double> H((size_t)(m + 1) * m, 0.0), h(m + 2);
-  XSB_CHK(vec_rander48(c, n, s.noise, t));
+  const Ranges rg = L.dist ? c->own_u : whole(n);
+  const int64_t soff = L.dist ? (int64_t)c->nsd * (2 * c->slab.e0) * L.nx * L.ny : 0;   // noise is a function of the GLOBAL dof index
+  XSB_CHK(vec_rander48(c, n, s.noise, t, soff));
   XSB_CHK(vec_pmult(c, n, L.idiag, t, V[0]));                       // v0 = M^-1 b (x0 = 0)
-  XSB_CHK(vec_mdot(c, n, V[0], V.data(), 0, true, c->scal));
+  XSB_CHK(vec_mdot(c, rg, V[0], V.data(), 0, true, c->scal));
   XSB_CHK(vec_fetch(c, c->scal, 1, h.data()));
   const double res0 = sqrt(h[0]); double res = res0;
   if (res0 == 0.0) return xsb_fail(c, XSB_ERR_BREAKDOWN, "zero noise vector in the Chebyshev eigenvalue estimate");
@@ -341,12 +416,11 @@ static int cheb_estimate(xsb_ctx c, Level &L)
   std::vector<double> cs(m + 1), sn(m + 1), rs(m + 1); rs[0] = res0;
   int it = 0;
   while (it < m) {
-    Epilogue ep;
-    XSB_CHK(spmv_baij(c, L.A, V[it], t, ep));
+    XSB_CHK(level_spmv(c, L, V[it], t));
     XSB_CHK(vec_pmult(c, n, L.idiag, t, V[it + 1]));               // w = M^-1 A v
-    XSB_CHK(vec_mdot(c, n, V[it + 1], V.data(), it + 1, false, c->scal));
+    XSB_CHK(vec_mdot(c, rg, V[it + 1], V.data(), it + 1, false, c->scal));
     XSB_CHK(vec_maxpy_dev(c, n, V[it + 1], V.data(), it + 1, c->scal, -1.0));
-    XSB_CHK(vec_mdot(c, n, V[it + 1], V.data(), 0, true, c->scal + it + 1));
+    XSB_CHK(vec_mdot(c, rg, V[it + 1], V.data(), 0, true, c->scal + it + 1));
     XSB_CHK(vec_scale_by_inv_sqrt(c, n, V[it + 1], c->scal + it + 1));
     XSB_CHK(vec_fetch(c, c->scal, it + 2, h.data()));
     const double tt = sqrt(h[it + 1]);
@@ -379,13 +453,15 @@ int mg_setup(xsb_ctx c)
   const SolverOpts &s = c->so; const int levels = s.mg_levels; const Lattice &Lt = c->lat;
   if (levels < 1 || levels > XSB_MAX_LEVELS) return xsb_fail(c, XSB_ERR_ARG, "-saddle_fieldsplit_u_pc_mg_levels %d out of range", levels);
   c->nlev = levels;
-  { Level &L = c->lev[levels - 1]; L = Level(); L.nx = Lt.NX; L.ny = Lt.NY; L.nz = Lt.NZ; L.A = c->A00; L.owns_A = false; }
+  const Slab &S = c->slab; const bool dist = S.nranks > 1;
+  if (dist && levels < 2) return xsb_fail(c, XSB_ERR_SUP, "the slab partition needs at least 2 MG levels (the coarse levels are replicated)");
+  { Level &L = c->lev[levels - 1]; L = Level(); L.nx = Lt.NX; L.ny = Lt.NY; L.nz = Lt.NZ; L.A = c->A00; L.owns_A = false; L.dist = dist; }
   for (int l = levels - 2; l >= 0; --l) {
     Level &F = c->lev[l + 1], &C = c->lev[l]; C = Level();
     int dims[3];
-    if (xsb_mg_level_dims(c->nsd, Lt.mx, Lt.my, Lt.mz, levels, l, dims)) return xsb_fail(c, XSB_ERR_ARG, "mesh %dx%dx%d cannot be coarsened to %d MG levels (DMCoarsen needs (n-1) divisible by 2)", Lt.mx, Lt.my, Lt.mz, levels);
+    if (xsb_mg_level_dims(c->nsd, Lt.mx, Lt.my, S.mz_glob, levels, l, dims)) return xsb_fail(c, XSB_ERR_ARG, "mesh %dx%dx%d cannot be coarsened to %d MG levels (DMCoarsen needs (n-1) divisible by 2)", Lt.mx, Lt.my, S.mz_glob, levels);
     C.nx = dims[0]; C.ny = dims[1]; C.nz = dims[2];
-    XSB_CHK(galerkin(c, F, C));
+    if (F.dist) XSB_CHK(galerkin_replicate(c, F, C)); else XSB_CHK(galerkin(c, F, C));
   }
   for (int l = 0; l < levels; ++l) {
     Level &L = c->lev[l]; const int64_t n = (int64_t)L.A.nb * L.A.bs;

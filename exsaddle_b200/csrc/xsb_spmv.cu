@@ -23,12 +23,12 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // ------------------------------------------------------------------ K1: CSR
 template <int UNROLL>
-__global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t n, const int *__restrict__ ia, const int *__restrict__ ja,
+__global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t row0, int64_t n, const int *__restrict__ ia, const int *__restrict__ ja,
                                                        const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t row = warp; row < n; row += nwarps) {
+  for (int64_t row = row0 + warp; row < row0 + n; row += nwarps) {
     const int k0 = ia[row], k1 = ia[row + 1];
     double acc = 0.0;
     int k = k0 + lane;
@@ -45,14 +45,15 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t n, const int *__r
   }
 }
 
-int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y)
+int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0, int64_t nrows)
 {
-  if (A.n == 0) return XSB_OK;
-  const int64_t warps = A.n; const int tpb = 256;
+  if (nrows < 0) nrows = A.n - row0;
+  if (nrows <= 0) return XSB_OK;
+  const int64_t warps = nrows; const int tpb = 256;
   int64_t blocks = (warps * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;   // persistent-style grid: 148 SMs x 8 resident CTAs x 16 waves
   if (blocks > cap) blocks = cap;
-  spmv_csr_kernel<8><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, x, y); KERNEL_OK();
+  spmv_csr_kernel<8><<<(unsigned)blocks, tpb, 0, c->stream>>>(row0, nrows, A.ia, A.ja, A.a, x, y); KERNEL_OK();
   return XSB_OK;
 }
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ double epilogue_value(const Epilogue &ep, int64_t i, 
 // with one coalesced value load, one block-column load, one x gather and one FMA per lane -- no per-element
 // div/mod, a single accumulator.  UN iterations are issued back to back so UN loads per lane are in flight.
 template <int BS, int UN>
-__global__ void __launch_bounds__(256) spmv_baij_kernel(int nb, const int *__restrict__ ia, const int *__restrict__ ja,
+__global__ void __launch_bounds__(256) spmv_baij_kernel(int node0, int nb, const int *__restrict__ ia, const int *__restrict__ ja,
                                                         const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y, Epilogue ep)
 {
   constexpr int BS2 = BS * BS, NBW = 32 / BS2, ACTIVE = NBW * BS2;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) spmv_baij_kernel(int nb, const int *__res
   const int g = lane / BS2, r = lane - g * BS2, ra = r / BS, ca = r - ra * BS;
   const bool active = lane < ACTIVE;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t node = warp; node < nb; node += nwarps) {
+  for (int64_t node = node0 + warp; node < node0 + nb; node += nwarps) {
     const int b0 = ia[node], nblk = ia[node + 1] - b0;
     const double *__restrict__ av = a + (int64_t)b0 * BS2 + lane;
     const int *__restrict__ cj = ja + b0 + g;
@@ -108,14 +109,15 @@ __global__ void __launch_bounds__(256) spmv_baij_kernel(int nb, const int *__res
   }
 }
 
-int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep)
+int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0, int nnodes)
 {
-  if (A.nb == 0) return XSB_OK;
-  const int tpb = 256; int64_t blocks = ((int64_t)A.nb * 32 + tpb - 1) / tpb;
+  if (nnodes < 0) nnodes = A.nb - node0;
+  if (nnodes <= 0) return XSB_OK;
+  const int tpb = 256; int64_t blocks = ((int64_t)nnodes * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;
   if (blocks > cap) blocks = cap;
-  if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
-  else if (A.bs == 2) spmv_baij_kernel<2, 4><<<(unsigned)blocks, tpb, 0, c->stream>>>(A.nb, A.ia, A.ja, A.a, x, y, ep);
+  if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
+  else if (A.bs == 2) spmv_baij_kernel<2, 4><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
   else return xsb_fail(c, XSB_ERR_SUP, "BAIJ block size %d", A.bs);
   KERNEL_OK();
   return XSB_OK;
@@ -132,7 +134,9 @@ int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Ep
     if (c->ev_used + 2 > c->evpool.size()) { for (int i = 0; i < 256; ++i) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); c->evpool.push_back(e); } }
     CUDA_OK(cudaEventRecord(c->evpool[c->ev_used], c->stream));
   }
-  if (c->so.matrix_free) XSB_CHK(mf_a00_apply(c, x, y, ep)); else XSB_CHK(spmv_baij(c, A, x, y, ep));
+  XSB_CHK(comm_halo_u(c, const_cast<double *>(x)));   // ghost planes of the input (no-op on one GPU)
+  if (c->so.matrix_free) XSB_CHK(mf_a00_apply(c, x, y, ep));
+  else { const int pn = c->lat.NX * c->lat.NY; XSB_CHK(spmv_baij(c, A, x, y, ep, c->slab.ou0 * pn, (c->slab.ou1 - c->slab.ou0) * pn)); }
   if (timed) { CUDA_OK(cudaEventRecord(c->evpool[c->ev_used + 1], c->stream)); c->ev_used += 2; }
   return XSB_OK;
 }

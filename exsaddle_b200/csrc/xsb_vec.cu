@@ -44,13 +44,15 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
 
 // partial[j*RB + block] = sum over the block's slice of w[i]*V_j[i]   (j < m)
 template <int M>
-__global__ void __launch_bounds__(RT) k_mdot_partial(int64_t n, const double *__restrict__ w, PtrPack V, double *__restrict__ partial)
+__global__ void __launch_bounds__(RT) k_mdot_partial(Ranges rg, const double *__restrict__ w, PtrPack V, double *__restrict__ partial)
 {
   __shared__ double sh[RT / 32];
   double acc[M];
 #pragma unroll
   for (int j = 0; j < M; ++j) acc[j] = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t n = rg.len0 + rg.len1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t < rg.len0 ? rg.off0 + t : rg.off1 + (t - rg.len0);   // owned entries only
     const double wi = w[i];
 #pragma unroll
     for (int j = 0; j < M; ++j) acc[j] += wi * V.p[j][i];
@@ -68,15 +70,15 @@ __global__ void __launch_bounds__(RT) k_reduce_final(int nb, const double *__res
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
-template <int M> static int mdot_launch(xsb_ctx c, int64_t n, const double *w, const PtrPack &P, double *out)
+template <int M> static int mdot_launch(xsb_ctx c, const Ranges &rg, const double *w, const PtrPack &P, double *out)
 {
-  k_mdot_partial<M><<<RB, RT, 0, c->stream>>>(n, w, P, c->red); KERNEL_OK();
+  k_mdot_partial<M><<<RB, RT, 0, c->stream>>>(rg, w, P, c->red); KERNEL_OK();
   k_reduce_final<<<M, RT, 0, c->stream>>>(RB, c->red, out); KERNEL_OK();
   return 0;
 }
 
 // out[j] = w . V[j] for j < k ; out[k] = w . w when with_norm (VecMDot + VecNorm^2 in one or few passes)
-int vec_mdot(xsb_ctx c, int64_t n, const double *w, double *const *V, int k, bool with_norm, double *out)
+int vec_mdot(xsb_ctx c, const Ranges &n, const double *w, double *const *V, int k, bool with_norm, double *out)
 {
   const int tot = k + (with_norm ? 1 : 0);
   for (int j0 = 0; j0 < tot; j0 += MD) {
@@ -94,7 +96,7 @@ int vec_mdot(xsb_ctx c, int64_t n, const double *w, double *const *V, int k, boo
     default: XSB_CHK(mdot_launch<8>(c, n, w, P, out + j0)); break;
     }
   }
-  return 0;
+  return comm_allreduce_sum(c, out, tot);   // VecMDot's MPI_Allreduce: one NCCL all-reduce of the whole block of partial sums
 }
 
 // w += sign * sum_j coef[j] V_j, applied in ascending j like a sequence of VecAXPY (VecMAXPY)
@@ -147,13 +149,15 @@ __global__ void k_scale_inv_sqrt(int64_t n, double *w, const double *nrm2)
 int vec_scale_by_inv_sqrt(xsb_ctx c, int64_t n, double *w, const double *nrm2) { k_scale_inv_sqrt<<<gridfor(n), RT, 0, c->stream>>>(n, w, nrm2); KERNEL_OK(); return 0; }
 
 // GCR update (KSPSolve_GCR_cycle): nrm = sqrt(v.v); a = (r.v)/nrm; v /= nrm; s /= nrm; x += a s; r -= a v; also ||r||^2
-__global__ void __launch_bounds__(RT) k_gcr_update(int64_t n, const double *__restrict__ dots, double *__restrict__ v, double *__restrict__ s,
+__global__ void __launch_bounds__(RT) k_gcr_update(Ranges rg, const double *__restrict__ dots, double *__restrict__ v, double *__restrict__ s,
                                                    double *__restrict__ x, double *__restrict__ r, double *__restrict__ partial)
 {
   __shared__ double sh[RT / 32];
   const double nrm = sqrt(dots[1]), a = dots[0] / nrm, inv = 1.0 / nrm;
   double acc = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t n = rg.len0 + rg.len1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t < rg.len0 ? rg.off0 + t : rg.off1 + (t - rg.len0);
     const double vi = v[i] * inv, si = s[i] * inv;
     v[i] = vi; s[i] = si;
     x[i] += a * si;
@@ -163,11 +167,11 @@ __global__ void __launch_bounds__(RT) k_gcr_update(int64_t n, const double *__re
   double t = block_sum(acc, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
-int vec_gcr_update(xsb_ctx c, int64_t n, const double *dots, double *v, double *s, double *x, double *r, double *rnorm2)
+int vec_gcr_update(xsb_ctx c, const Ranges &rg, const double *dots, double *v, double *s, double *x, double *r, double *rnorm2)
 {
-  k_gcr_update<<<RB, RT, 0, c->stream>>>(n, dots, v, s, x, r, c->red); KERNEL_OK();
+  k_gcr_update<<<RB, RT, 0, c->stream>>>(rg, dots, v, s, x, r, c->red); KERNEL_OK();
   k_reduce_final<<<1, RT, 0, c->stream>>>(RB, c->red, rnorm2); KERNEL_OK();
-  return 0;
+  return comm_allreduce_sum(c, rnorm2, 1);
 }
 
 int vec_fetch(xsb_ctx c, const double *dev, int n, double *host)
@@ -209,12 +213,12 @@ int vec_diagnostics(xsb_ctx c, const double *x, double *out_dev)
 // ------------------------------------------------------------------ PetscRandom "rander48" stream on the device
 // value i = X_{i+1} / 2^48 with X_{k+1} = (a X_k + c) mod 2^48, X_0 = 0x12345678<<16 | 0x330E (drand48 seeding);
 // each thread jumps ahead with the composed affine map and then walks 64 consecutive values.
-__global__ void k_rander48(int64_t n, int interval, double *x)
+__global__ void k_rander48(int64_t n, int interval, double *x, int64_t soff)
 {
   const uint64_t a = 0x5DEECE66DULL, cc = 0xBULL, mask = (1ULL << 48) - 1;
   const int64_t chunk = 64, i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * chunk;
   if (i0 >= n) return;
-  uint64_t A = 1, C = 0, pa = a, pc = cc; uint64_t k = (uint64_t)i0;   // f^k = A x + C
+  uint64_t A = 1, C = 0, pa = a, pc = cc; uint64_t k = (uint64_t)(i0 + soff);   // f^k = A x + C; soff = global index of local entry 0
   while (k) { if (k & 1) { A = (A * pa) & mask; C = (C * pa + pc) & mask; } pc = (pc * pa + pc) & mask; pa = (pa * pa) & mask; k >>= 1; }
   uint64_t X = (A * ((0x12345678ULL << 16) | 0x330EULL) + C) & mask;
   for (int64_t i = i0; i < n && i < i0 + chunk; ++i) {
@@ -223,9 +227,9 @@ __global__ void k_rander48(int64_t n, int interval, double *x)
     x[i] = interval ? 2.0 * u - 1.0 : u;
   }
 }
-int vec_rander48(xsb_ctx c, int64_t n, int interval, double *x)
+int vec_rander48(xsb_ctx c, int64_t n, int interval, double *x, int64_t soff)
 {
   const int64_t threads = (n + 63) / 64;
-  k_rander48<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(n, interval, x); KERNEL_OK();
+  k_rander48<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(n, interval, x, soff); KERNEL_OK();
   return 0;
 }

@@ -130,6 +130,18 @@ int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, in
 /* Element z-range [k0,k1) owned by `rank` of `nranks` (elements split like the reference's pressure rule,
    femixedspace.c:1231-1240: mz/nranks each, remainder to the low ranks). */
 int xsb_slab_range(int mz, int nranks, int rank, int *k0, int *k1);
+/* host-only: the partition xsb_get_partition reports, computed from the mesh alone (same out[12] layout) */
+int xsb_slab_layout(int nsd, int mx, int my, int mz, int nranks, int rank, int64_t out[12]);
+/* NCCL bootstrap (one process per GPU; replaces MPI_Init/PETSC_COMM_WORLD of the reference, femixedspace.c:645,684):
+   rank 0 calls xsb_comm_unique_id and ships the 128 bytes to the other ranks (the launcher's store, MPI or a file);
+   every rank then calls xsb_comm_init BEFORE xsb_assemble.  nranks = 1 is a no-op. */
+int xsb_comm_unique_id(void *out128);
+int xsb_comm_init(xsb_ctx ctx, const void *unique_id, int rank, int nranks);
+/* partition of this rank after xsb_assemble: out[0]=rank [1]=nranks [2..3]=owned element layers [k0,k1)
+   [4..5]=local lattice layers [e0,e1) [6]=offset,[7]=length of the owned velocity entries in a local vector
+   [8],[9]= same for the owned pressure entries [10],[11]=global (one-rank DMComposite) index of the first owned
+   velocity / pressure dof.  Local vectors are [u_local | p_local] on the local lattice (ghost planes included). */
+int xsb_get_partition(xsb_ctx ctx, int64_t out[12]);
 
 #ifdef __cplusplus
 }
