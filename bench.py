@@ -8,8 +8,8 @@ set-up is outside the timed region).  Inputs (A00 alone is 10.4 GB at 64^3) are 
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--mx 64] [--eta1 1e6] [--levels 6] [--impl reference]
 
-N > 1 (torchrun): every rank solves its own independent replica of the workload (weak scaling, no collective on
-the data path; the slab-partitioned single-problem solve is not in this round) and value = mean solve time.
+N > 1 (torchrun): the SAME problem is cut into z-slabs, one per GPU (strong scaling): NCCL halo exchange in front of
+every operator apply, NCCL all-reduce behind every Krylov reduction; value = solve time, max over ranks.
 """
 import argparse
 import json
@@ -144,10 +144,11 @@ def main():
     ap.add_argument("--no-matrix-free", dest="no_matrix_free", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
     cfg = {"workload": workload_name(a), "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
-           "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one per GPU), no data-path collective" % world,
+           "parallelism": "1 GPU" if world == 1 else "one problem, z-slab partition over %d GPUs (one process per GPU): NCCL send/recv halo exchange before every operator apply, NCCL all-reduce for Krylov dot products; fine MG level distributed, coarse levels replicated, ILU(0) per rank (bjacobi)" % world,
            "l2": "inputs (A00 BAIJ 10.4 GB at 64^3) far exceed the 126 MB L2; no flush needed",
            "options": workload_options(a)}
 
@@ -157,7 +158,7 @@ def main():
         base, per_outer, t_setup = cpu_reference(a, max(1, a.steps), a.warmup, None)
         line = {"impl": "reference", "metric": "stokes_ksp_solve_time_rtol1e-8", "value": base["value"], "unit": "s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": None if base["value"] is None else 1e3 * base["value"],
-                "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line)); return 0
@@ -174,7 +175,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     g = X.ExSaddle(workload_options(a) + " -xsb_time_kernels", nsd=3, device=local)
+    if world > 1:   # one problem, z-slabs over the ranks: NCCL communicator inside the library, id shipped by torch.distributed
+        uid = [X.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(uid[0], rank, world)
     t0 = time.time(); g.assemble(); t_asm = time.time() - t0
+    part = g.partition()
+    own_frac = part["u_len"] / float(g.nu)   # share of the local lattice this rank owns (ghost layers excluded)
     t0 = time.time(); g.ksp_setup(); t_setup = time.time() - t0
     n = g.n
     stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local))
@@ -248,27 +255,29 @@ def main():
               "a00_apply_avg_us": cm["a00_avg_ns"] / 1e3, "a00_apply_gflops": (2 * 5900.0 * nel) / max(cm["a00_avg_ns"], 1),
               "note": "fine-level A00 products by the sum-factorised Q2 element kernel (FP64-issue bound: ~5.9 kFMA/element, 16 B/dof of HBM traffic); coarse levels and the outer MatMult stay assembled"}
 
+    # collective on slabs (halo exchange inside): every rank runs it
+    a_info = g.mat_info(X.MAT_A)
+    # full-A AIJ MatMult micro-measure (the reference's MATAIJ layout): 20 warm-up + 50 timed applies
+    xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
+    yout = torch.empty_like(xin)
+    with torch.cuda.stream(stream):
+        for _ in range(10):
+            g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for _ in range(30):
+            g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
+        m1.record(stream)
+    torch.cuda.synchronize()
+    aij_ms = m0.elapsed_time(m1) / 30
+
     if rank == 0:
         peak, peak_src = peaks()
         info = g.mat_info(X.MAT_A00)
-        bytes_launch = a00_bytes(info, a00_modes)
+        bytes_launch = a00_bytes(info, a00_modes) * own_frac   # owned rows only are streamed (own_frac = 1 on one GPU)
         avg_ns = sum(a00_ns) / len(a00_ns)
         achieved = bytes_launch / avg_ns if avg_ns else 0.0   # B/ns = GB/s
-        a_info = g.mat_info(X.MAT_A)
-        # full-A AIJ MatMult micro-measure (the reference's MATAIJ layout): 20 warm-up + 50 timed applies
-        xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
-        yout = torch.empty_like(xin)
-        with torch.cuda.stream(stream):
-            for _ in range(10):
-                g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            m0.record(stream)
-            for _ in range(30):
-                g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
-            m1.record(stream)
-        torch.cuda.synchronize()
-        aij_ms = m0.elapsed_time(m1) / 30
-        aij_bytes = 12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]
+        aij_bytes = (12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]) * own_frac
         roof = {"bound": "hbm", "kernel": "spmv_baij_kernel<3> (fine-level A00 with fused residual/Chebyshev epilogue)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
@@ -294,7 +303,7 @@ def main():
             except Exception as e:   # the checker must never take the bench line down
                 base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
         line = {"metric": "stokes_ksp_solve_time_rtol1e-8", "value": sec_per_solve, "unit": "s", "n_gpus": world, "steps": a.steps,
-                "warmup": warmup, "ms_per_step": 1e3 * sec_per_solve, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+                "warmup": warmup, "ms_per_step": 1e3 * sec_per_solve, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
                 "solve": {"outer_its": its, "reason": reason, "inner_gcr_its": int(sum(inner)), "rnorm0": float(hist[0]), "rnorm": float(hist[-1]),
                           "a00_spmv_per_solve": n_a00 // a.steps, "assemble_s": t_asm, "ksp_setup_s": t_setup},
