@@ -108,6 +108,7 @@ struct Level {
   double emin = 0, emax = 0, emin_est = NAN, emax_est = NAN;
   double *x = nullptr, *b = nullptr, *r = nullptr, *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
   double *inv = nullptr;      // dense inverse of the coarsest operator
+  bool rowpart = false; int rp0 = 0, rp1 = 0;   // replicated level whose products are computed plane range [rp0,rp1) per rank, then all-gathered
   bool dist = false;          // z-slab distributed level (vectors on the local lattice, ghost planes, owned-row products)
 };
 
@@ -137,6 +138,9 @@ struct SolverOpts {
   int n_cheb_fixed = 0; double cheb_emin[XSB_MAX_LEVELS], cheb_emax[XSB_MAX_LEVELS];
   int p_pc = 0;          // 0 ilu0 (bjacobi) 1 jacobi
   int time_kernels = 0;
+  int mf_kernel = 3;     // -xsb_mf_kernel: 1 = 9 lanes per element, 2 / 3 = 3 lanes per element with preloaded / reduction scatter (xsb_mf.cu)
+  int mf_reverse = 1;    // -xsb_mf_reverse: successive colour launches sweep the mesh in alternating directions (L2 reuse)
+  int mf_chunk = 0;      // -xsb_mf_chunk: element layers per z-chunk of the matrix-free apply (0 = sized for L2)
   int matrix_free = 0;   // -xsb_matrix_free: fine-level A00 products by the sum-factorised element kernel (xsb_mf.cu)
 };
 
@@ -164,7 +168,7 @@ struct xsb_ctx_s {
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
-  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr;
+  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr;
   double *red = nullptr;      // device reduction scratch
   double *red_h = nullptr;    // pinned host mirror
   double *scal = nullptr;     // device scalars (dot results consumed by kernels)
@@ -229,6 +233,7 @@ int comm_halo_p(xsb_ctx c, double *p);            // pressure ghost planes (1 be
 int comm_halo_full(xsb_ctx c, double *x);         // [u|p]
 int comm_bcast_segments(xsb_ctx c, double *glob, const int64_t *offs /* nranks+1 */);
 int comm_bcast_planes(xsb_ctx c, double *glob, int64_t plane_doubles, int nplanes_glob);   // every rank contributes its owned coarse planes
+int comm_allgather_planes(xsb_ctx c, double *glob, int64_t plane_doubles, int nplanes);    // rank r contributes planes [r*n/N, (r+1)*n/N)
 inline Ranges whole(int64_t n) { Ranges r; r.len0 = n; return r; }
 // ---- xsb_mg.cu
 int mg_setup(xsb_ctx c);

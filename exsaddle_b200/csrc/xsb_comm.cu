@@ -141,3 +141,20 @@ int comm_bcast_planes(xsb_ctx c, double *glob, int64_t pd, int nplanes_glob)
   NCCL_OK(g_nccl.GroupEnd());
   return 0;
 }
+
+// Row-partitioned product on a replicated level: rank r holds fresh values for planes [r*n/N, (r+1)*n/N) of `glob`
+int comm_allgather_planes(xsb_ctx c, double *glob, int64_t pd, int nplanes)
+{
+  const Slab &S = c->slab;
+  if (S.nranks == 1) return 0;
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  NCCL_OK(g_nccl.GroupStart());
+  for (int r = 0; r < S.nranks; ++r) {
+    const int64_t p0 = (int64_t)r * nplanes / S.nranks, p1 = (int64_t)(r + 1) * nplanes / S.nranks;
+    if (p1 <= p0) continue;
+    double *p = glob + p0 * pd;
+    NCCL_OK(g_nccl.Broadcast(p, p, (size_t)((p1 - p0) * pd), ncclFloat64_, r, comm, c->stream));
+  }
+  NCCL_OK(g_nccl.GroupEnd());
+  return 0;
+}

@@ -323,7 +323,13 @@ __global__ void k_cheb_first_zero(int64_t n, double scale, const double *__restr
 
 static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, double *y, const Epilogue &ep)
 {
-  return fine ? spmv_a00_fine(c, L.A, x, y, ep) : spmv_baij(c, L.A, x, y, ep);
+  if (fine) return spmv_a00_fine(c, L.A, x, y, ep);
+  if (!L.rowpart) return spmv_baij(c, L.A, x, y, ep);
+  // replicated level, row-partitioned product: this rank computes its share of the node planes (rows and fused
+  // epilogue are per row, so the values are bitwise those of the replicated product), then all ranks exchange planes
+  const int pn = L.nx * L.ny;
+  XSB_CHK(spmv_baij(c, L.A, x, y, ep, L.rp0 * pn, (L.rp1 - L.rp0) * pn));
+  return comm_allgather_planes(c, y, (int64_t)L.A.bs * pn, L.nz);
 }
 // set-up products (eigenvalue estimate): not counted; slab levels refresh ghosts and compute owned rows only
 static int level_spmv(xsb_ctx c, const Level &L, const double *x, double *y)
@@ -468,6 +474,15 @@ int mg_setup(xsb_ctx c)
     XSB_CHK(dev_alloc(c, &L.x, (size_t)n)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)n));
     XSB_CHK(dev_alloc(c, &L.w0, (size_t)n)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)n)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
     XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
+  }
+  // large replicated levels: split the rows of every smoother / residual product over the ranks (-xsb_rowpart_min_nodes)
+  if (dist) {
+    const int64_t min_nodes = c->opt.integer("xsb_rowpart_min_nodes", 100000);
+    for (int l = 1; l < levels - 1; ++l) {
+      Level &L = c->lev[l];
+      if ((int64_t)L.A.nb < min_nodes || L.nz < S.nranks) continue;
+      L.rowpart = true; L.rp0 = (int)((int64_t)S.rank * L.nz / S.nranks); L.rp1 = (int)((int64_t)(S.rank + 1) * L.nz / S.nranks);
+    }
   }
   XSB_CHK(coarse_invert(c, c->lev[0]));
   for (int l = 1; l < levels; ++l) {

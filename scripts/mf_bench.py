@@ -1,15 +1,18 @@
-"""Matrix-free vs assembled A00 apply timing (development aid): python scripts/mf_bench.py MX"""
+"""Matrix-free vs assembled A00 apply timing (development aid): python scripts/mf_bench.py MX [reps] ["extra options"]
+Times the assembled BAIJ product and both matrix-free kernels (-xsb_mf_kernel 1|2) on the same input."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import exsaddle_b200 as X
 mx = int(sys.argv[1]); reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-g = X.ExSaddle("-mx %d -model 6 -eta1 1e6" % mx, nsd=3).assemble()
-st = torch.cuda.ExternalStream(g.stream())
-rows = g.mat_info(X.MAT_A00)[0]
-x = torch.sin(0.37 * torch.arange(rows, dtype=torch.float64, device="cuda")) + 0.1
+more = " " + sys.argv[3] if len(sys.argv) > 3 else ""
 out = {}
-for name, which in (("A00_baij", X.MAT_A00), ("A00_mf", X.MAT_A00_MF)):
+ref = None
+for name, which, extra in (("A00_baij", X.MAT_A00, ""), ("A00_mf_v1", X.MAT_A00_MF, " -xsb_mf_kernel 1"), ("A00_mf_v2", X.MAT_A00_MF, " -xsb_mf_kernel 2"), ("A00_mf_v3", X.MAT_A00_MF, " -xsb_mf_kernel 3")):
+    g = X.ExSaddle("-mx %d -model 6 -eta1 1e6%s%s" % (mx, extra, more), nsd=3).assemble()
+    st = torch.cuda.ExternalStream(g.stream())
+    rows = g.mat_info(X.MAT_A00)[0]
+    x = torch.sin(0.37 * torch.arange(rows, dtype=torch.float64, device="cuda")) + 0.1
     y = torch.empty(rows, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
     with torch.cuda.stream(st):
@@ -21,7 +24,10 @@ for name, which in (("A00_baij", X.MAT_A00), ("A00_mf", X.MAT_A00_MF)):
             g.mat_mult_dev(which, x.data_ptr(), y.data_ptr())
         e1.record(st)
     torch.cuda.synchronize()
-    out[name] = {"ms": e0.elapsed_time(e1) / reps, "checksum": float(y.double().norm())}
-nel = mx ** 3
-out["A00_mf"]["GFLOPs"] = 2 * 5900 * nel / out["A00_mf"]["ms"] / 1e6
+    if ref is None:
+        ref = y.clone()
+    out[name] = {"ms": e0.elapsed_time(e1) / reps, "rel_diff_vs_baij": float((y - ref).norm() / ref.norm())}
+    if "mf" in name:
+        out[name]["GFLOPs"] = 2 * 5900 * mx ** 3 / out[name]["ms"] / 1e6
+    g.close(); del x, y
 print(json.dumps(out))

@@ -269,8 +269,9 @@ def test_32cubed_properties():
 @pytest.mark.parametrize("opts,lame", [("-model 6 -mx 4 -eta1 1e4", False), ("-model 1 -mx 3 -my 5 -mz 2 -eta1 10", False),
                                        ("-model 11 -size_x 0.1 -mx 6", False), ("-model 0 -mx 5 -size_z 0.3 -freesliphack", False),
                                        ("-model 12 -mx 4 -mu1 10", True), ("-model 2 -mx 1", False)])
-def test_matrix_free_apply_matches_assembled_block(opts, lame):
-    g = X.ExSaddle(opts, nsd=3, lame=lame).assemble()
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_matrix_free_apply_matches_assembled_block(opts, lame, kernel):
+    g = X.ExSaddle(opts + " -xsb_mf_kernel %d" % kernel, nsd=3, lame=lame).assemble()
     o = O.Problem(opts, nsd=3, lame=lame)
     A00 = o.submatrix(0, 0).scipy()
     rng = np.random.default_rng(2)
