@@ -97,6 +97,15 @@ HD int box_slot(const BoxPattern &p, int i, int j, int k, int gi, int gj, int gk
   return ((gk - l2) * (h1 - l1 + 1) + (gj - l1)) * (h0 - l0 + 1) + (gi - l0);
 }
 
+// FE tables of the uniform box mesh (host_tables in xsb_fe.cu), kept on the device for the element kernels
+struct FeTables {
+  double wq[27];            // product Gauss weights (literals of femixedspace.c:1379-1380)
+  double Nu[27][27];        // Q2 basis at quadrature points [q][i]
+  double Gu[27][27][3];     // Q2 global derivatives d/dx_d  [q][i][d] = dN/dxi_d / h_d
+  double Np[27][8];         // Q1 basis [q][i]
+  double detJ;              // h_x h_y (h_z)
+};
+
 struct Csr  { int n = 0, m = 0; int64_t nnz = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; };
 // BAIJ: block rows = lattice nodes, blocks bs x bs stored row-major, block columns ascending.
 struct Baij { int nb = 0, bs = 0; int64_t nblk = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; BoxPattern pat{0, 0, 0, 0}; };
@@ -154,6 +163,7 @@ struct xsb_ctx_s {
   Model mdl;
   SolverOpts so;
   bool assembled = false, ksp_ready = false;
+  bool no_A = false;   // -xsb_matrix_free full: A and A00 are never stored (operator-free fine level)
   // FE data (device)
   double *coeff = nullptr;       // [slot][nel*nqp]
   double *coeff_nodal = nullptr; // [slot][npn]
@@ -200,13 +210,17 @@ int bc_list_faces(int nsd, int lame, int model, int freeslip, int mx, int my, in
 // ---- xsb_spmv.cu
 enum { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_CHEB_FIRST = 2, EPI_CHEB = 3 };
 struct Epilogue { int mode = EPI_PLAIN; const double *b = nullptr, *idiag = nullptr, *pk = nullptr, *pkm1 = nullptr; double s0 = 0, s1 = 0, s2 = 0; };
-int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0 = 0, int64_t nrows = -1);
+int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0 = 0, int64_t nrows = -1, const double *yadd = nullptr);   // y = A x (+ yadd)
 int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0 = 0, int nnodes = -1);
 int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);   // counted (+ timed) fine-level launch
 int spmv_collect_timing(xsb_ctx c);
 // ---- xsb_mf.cu
 int mf_setup(xsb_ctx c);
 int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep);
+int mf_a00_apply_raw(xsb_ctx c, const double *x, double *y);   // without the Dirichlet rows / columns (A before MatZeroRowsColumns)
+// ---- xsb_mfull.cu (operator-free mode)
+int mf_diag_inv(xsb_ctx c, double *idiag);                    // 1 / diag(A00) from the element matrices
+int galerkin_elements(xsb_ctx c, Level &C);                   // P^T A00 P assembled element by element on the local lattice
 // ---- xsb_vec.cu
 int vec_set(xsb_ctx c, int64_t n, double a, double *x);
 int vec_copy(xsb_ctx c, int64_t n, const double *x, double *y);

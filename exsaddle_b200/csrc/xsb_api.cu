@@ -179,6 +179,7 @@ static int pick_csr(xsb_ctx c, int which, const Csr **S, const Baij **B)
 {
   *S = nullptr; *B = nullptr;
   if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "matrix requested before xsb_assemble");
+  if (c->no_A && (which == XSB_MAT_A || which == XSB_MAT_A00)) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free full: A and A00 are not stored (use xsb_mat_mult, or XSB_MAT_A00_MF)");
   switch (which) {
   case XSB_MAT_A: *S = &c->A; return 0;
   case XSB_MAT_A00: case XSB_MAT_A00_MF: *B = &c->A00; return 0;
@@ -195,6 +196,11 @@ static int pick_csr(xsb_ctx c, int which, const Csr **S, const Baij **B)
 int xsb_mat_get_info(xsb_ctx c, int which, int64_t *rows, int64_t *cols, int64_t *nnz, int *bs)
 {
   NEED_DEVICE(c);
+  if (c->no_A && c->assembled && (which == XSB_MAT_A || which == XSB_MAT_A00)) {   // sizes of the operators that are applied but not stored
+    const int64_t n = which == XSB_MAT_A ? c->lat.n : c->lat.nu;
+    if (rows) *rows = n; if (cols) *cols = n; if (nnz) *nnz = which == XSB_MAT_A ? c->A.nnz : 0; if (bs) *bs = which == XSB_MAT_A ? 1 : c->nsd;
+    return XSB_OK;
+  }
   const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
   if (S) { if (rows) *rows = S->n; if (cols) *cols = S->m; if (nnz) *nnz = S->nnz; if (bs) *bs = 1; }
   else { if (rows) *rows = (int64_t)B->nb * B->bs; if (cols) *cols = (int64_t)B->nb * B->bs; if (nnz) *nnz = B->nblk * B->bs * B->bs; if (bs) *bs = B->bs; }
@@ -218,6 +224,10 @@ int xsb_mat_get_csr(xsb_ctx c, int which, int32_t *ia, int32_t *ja, double *a)
 int xsb_mat_mult_dev(xsb_ctx c, int which, const double *x, double *y)
 {
   NEED_DEVICE(c);
+  if (c->no_A && c->assembled) {
+    if (which == XSB_MAT_A) return op_full_mult(c, x, y);
+    if (which == XSB_MAT_A00) which = XSB_MAT_A00_MF;
+  }
   const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
   if (S) return which == XSB_MAT_A ? op_full_mult(c, x, y) : spmv_csr(c, *S, x, y);
   Epilogue ep;

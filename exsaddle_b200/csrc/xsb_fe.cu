@@ -14,14 +14,6 @@
 #include <cstdarg>
 
 // ------------------------------------------------------------------ tables
-struct FeTables {
-  double wq[27];            // product Gauss weights (literals of femixedspace.c:1379-1380)
-  double Nu[27][27];        // Q2 basis at quadrature points [q][i]
-  double Gu[27][27][3];     // Q2 global derivatives d/dx_d  [q][i][d] = dN/dxi_d / h_d
-  double Np[27][8];         // Q1 basis [q][i]
-  double detJ;              // h_x h_y (h_z)
-};
-
 static void host_tables(const Lattice &L, FeTables &T)
 {
   static const double xi1d[3] = {-0.774596669241483, 0.0, 0.774596669241483};
@@ -356,9 +348,12 @@ __global__ void mp_ja_kernel(Lattice L, const int *ia, int *ja)
 // read-modify-write of the global values needs no atomics; colours run in a fixed order, hence the
 // result is bit-reproducible.  Per matrix entry the quadrature sum runs q = 0..nqp-1 with the
 // surviving B^T D B terms in the reference's k order (femixedspace.c:2531-2559).
-template <int NSD>
+// SPLIT (operator-free mode, -xsb_matrix_free full): the velocity block is never formed; the gradient / divergence /
+// pressure blocks go straight into their own CSR arrays (same values, same colour order).
+struct SplitDst { const int *ia01, *ia10, *ia11; double *a01, *a10, *a11; };
+template <int NSD, bool SPLIT>
 __global__ void __launch_bounds__(256) assemble_kernel(Lattice L, int lame, int colour, const FeTables *T, const double *coeff,
-                                                       const int *ia, double *a, const int *mia, double *ma, double *F)
+                                                       const int *ia, double *a, const int *mia, double *ma, double *F, SplitDst sp)
 {
   constexpr int NBU = NSD == 3 ? 27 : 9, NBP = NSD == 3 ? 8 : 4, NQP = NBU;
   __shared__ double sG[NQP][NBU][NSD];
@@ -388,7 +383,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(Lattice L, int lame, int 
   __syncthreads();
   const int nK = NSD == 3 ? 3 : 1;
   // ---- A11: one thread per (node i, node j) pair -> NSD x NSD block
-  for (int pr = tid; pr < NBU * NBU; pr += blockDim.x) {
+  for (int pr = tid; !SPLIT && pr < NBU * NBU; pr += blockDim.x) {
     const int i = pr / NBU, j = pr - i * NBU;
     double r[NSD][NSD];
 #pragma unroll
@@ -445,9 +440,15 @@ __global__ void __launch_bounds__(256) assemble_kernel(Lattice L, int lame, int 
     const int64_t pnode = pi + (int64_t)pj * L.PX + (int64_t)pk * L.PX * L.PY;
     const int pp = NSD * bu.ncu + box_ppos(bu, pi, pj, pk);
     const int upos = NSD * box_upos(bp, gi, gj, gk);
-    double *prow = a + ia[L.nu + pnode] + upos;
+    if (SPLIT) {
+      double *prow = sp.a10 + sp.ia10[pnode] + upos; const int ppos = box_ppos(bu, pi, pj, pk);
 #pragma unroll
-    for (int d = 0; d < NSD; ++d) { a[ia[NSD * node + d] + pp] += g[d]; prow[d] += g[d]; }   // A21 = A12^T (:2584-2590)
+      for (int d = 0; d < NSD; ++d) { sp.a01[sp.ia01[NSD * node + d] + ppos] += g[d]; prow[d] += g[d]; }
+    } else {
+      double *prow = a + ia[L.nu + pnode] + upos;
+#pragma unroll
+      for (int d = 0; d < NSD; ++d) { a[ia[NSD * node + d] + pp] += g[d]; prow[d] += g[d]; }   // A21 = A12^T (:2584-2590)
+    }
   }
   // ---- A22 (LAME) and Mpscaled: one thread per (pressure node i, pressure node j)
   for (int pr = tid; pr < NBP * NBP; pr += blockDim.x) {
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(Lattice L, int lame, int 
     RowBox bp; row_box_p(L, pi, pj, pk, bp);
     const int64_t pnode = pi + (int64_t)pj * L.PX + (int64_t)pk * L.PX * L.PY;
     const int pos = box_ppos(bp, qi, qj, qk);
-    if (lame) a[ia[L.nu + pnode] + NSD * bp.ncu + pos] += a22;
+    if (lame) { if (SPLIT) sp.a11[sp.ia11[pnode] + pos] += a22; else a[ia[L.nu + pnode] + NSD * bp.ncu + pos] += a22; }
     ma[mia[pnode] + pos] += s;
   }
   // ---- F1 / F2 (:2695-2710, :2763-2778)
@@ -550,6 +551,24 @@ __global__ void sub_fill_kernel(Lattice L, int64_t r0, int64_t nr, int pcols, co
   for (int k = lane; k < cnt; k += 32) { sja[sia[t] + k] = ja[src + k] - shift; sa[sia[t] + k] = a[src + k]; }
 }
 
+// closed-form columns of a sub-block row (operator-free mode: there is no AIJ row to copy from)
+__global__ void sub_ja_kernel(Lattice L, int64_t r0, int64_t nr, int pcols, const int *sia, int *sja)
+{
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (t >= nr) return;
+  RowBox b; int comp; row_to_box(L, r0 + t, b, &comp);
+  int c = sia[t];
+  if (pcols) { for (int kk = b.plo[2]; kk <= b.phi[2]; ++kk) for (int jj = b.plo[1]; jj <= b.phi[1]; ++jj) for (int ii = b.plo[0]; ii <= b.phi[0]; ++ii) sja[c++] = ii + jj * L.PX + kk * L.PX * L.PY; }
+  else { for (int kk = b.ulo[2]; kk <= b.uhi[2]; ++kk) for (int jj = b.ulo[1]; jj <= b.uhi[1]; ++jj) for (int ii = b.ulo[0]; ii <= b.uhi[0]; ++ii) for (int d = 0; d < L.nsd; ++d) sja[c++] = L.nsd * (ii + jj * L.NX + kk * L.NX * L.NY) + d; }
+}
+// MatZeroRowsColumns on the off-diagonal blocks: A01 loses the rows, A10 the columns of the constrained velocity dofs
+__global__ void zero_split_kernel(int64_t nr, int rows_are_u, const int *ia, const int *ja, double *a, const unsigned char *isbc)
+{
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; int lane = threadIdx.x & 31;
+  if (row >= nr) return;
+  const bool rb = rows_are_u && isbc[row];
+  for (int k = ia[row] + lane; k < ia[row + 1]; k += 32) if (rb || (!rows_are_u && isbc[ja[k]])) a[k] = 0.0;
+}
+
 // ------------------------------------------------------------------ helpers
 static int scan_to_ia(xsb_ctx c, int64_t n, int64_t *len64 /* n+1, device, len in [0,n) */, int **ia_out, int64_t *total)
 {
@@ -590,14 +609,40 @@ int fe_assemble(xsb_ctx c)
   coeff_eval_kernel<<<nblk(nq), 256, 0, st>>>(L, c->mdl, c->lame, dT, c->coeff); KERNEL_OK();
   q1_project_kernel<<<nblk(L.npn, 128), 128, 0, st>>>(L, dT, c->coeff, c->coeff_nodal); KERNEL_OK();
   q1_interp_kernel<<<nblk(nq), 256, 0, st>>>(L, dT, c->coeff_nodal, c->coeff); KERNEL_OK();
+  // operator-free mode (-xsb_matrix_free full): A and A00 are never stored (128^3: nnz(A) = 1.13e10 > 2^31 and 137 GB)
+  { const std::string mfv = c->opt.str("xsb_matrix_free", "0"); c->no_A = (mfv == "full" || mfv == "2"); }
+  const bool split = c->no_A;
+  if (split && nsd != 3) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free full is implemented for the 3-D executables");
   // AIJ pattern
   int64_t *len64 = nullptr; CUDA_OK(cudaMalloc(&len64, sizeof(int64_t) * (L.n + 1)));
   row_len_kernel<<<nblk(L.n), 256, 0, st>>>(L, len64); KERNEL_OK();
   c->A.n = c->A.m = (int)L.n;
-  { int rc = scan_to_ia(c, L.n, len64, &c->A.ia, &c->A.nnz); if (rc) { cudaFree(len64); return rc; } }
-  XSB_CHK(dev_alloc(c, &c->A.ja, (size_t)c->A.nnz)); XSB_CHK(dev_alloc(c, &c->A.a, (size_t)c->A.nnz));
-  fill_ja_kernel<<<nblk(L.n * 32), 256, 0, st>>>(L, c->A.ia, c->A.ja); KERNEL_OK();
-  CUDA_OK(cudaMemsetAsync(c->A.a, 0, sizeof(double) * c->A.nnz, st));
+  SplitDst sp{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  struct SubDef { Csr *S; int64_t r0, nr; int pcols; };
+  SubDef subs[3] = {{&c->A01, 0, L.nu, 1}, {&c->A10, L.nu, L.np, 0}, {&c->A11, L.nu, L.np, 1}};
+  if (!split) {
+    { int rc = scan_to_ia(c, L.n, len64, &c->A.ia, &c->A.nnz); if (rc) { cudaFree(len64); return rc; } }
+    XSB_CHK(dev_alloc(c, &c->A.ja, (size_t)c->A.nnz)); XSB_CHK(dev_alloc(c, &c->A.a, (size_t)c->A.nnz));
+    fill_ja_kernel<<<nblk(L.n * 32), 256, 0, st>>>(L, c->A.ia, c->A.ja); KERNEL_OK();
+    CUDA_OK(cudaMemsetAsync(c->A.a, 0, sizeof(double) * c->A.nnz, st));
+  } else {
+    {   // nnz(A) is still reported (xsb_get_sizes): total of the closed-form row lengths
+      void *tmp = nullptr; size_t tb = 0; int64_t *tot = nullptr; CUDA_OK(cudaMalloc(&tot, sizeof(int64_t)));
+      CUDA_OK(cub::DeviceReduce::Sum(nullptr, tb, len64, tot, L.n, st)); CUDA_OK(cudaMalloc(&tmp, tb));
+      CUDA_OK(cub::DeviceReduce::Sum(tmp, tb, len64, tot, L.n, st));
+      CUDA_OK(cudaMemcpyAsync(&c->A.nnz, tot, sizeof(int64_t), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+      CUDA_OK(cudaFree(tmp)); CUDA_OK(cudaFree(tot));
+    }
+    for (auto &s : subs) {
+      sub_len_kernel<<<nblk(s.nr), 256, 0, st>>>(L, s.r0, s.nr, s.pcols, len64); KERNEL_OK();
+      s.S->n = (int)s.nr; s.S->m = s.pcols ? (int)L.np : (int)L.nu;
+      { int rc = scan_to_ia(c, s.nr, len64, &s.S->ia, &s.S->nnz); if (rc) { cudaFree(len64); return rc; } }
+      XSB_CHK(dev_alloc(c, &s.S->ja, (size_t)s.S->nnz)); XSB_CHK(dev_alloc(c, &s.S->a, (size_t)s.S->nnz));
+      sub_ja_kernel<<<nblk(s.nr), 256, 0, st>>>(L, s.r0, s.nr, s.pcols, s.S->ia, s.S->ja); KERNEL_OK();
+      CUDA_OK(cudaMemsetAsync(s.S->a, 0, sizeof(double) * s.S->nnz, st));
+    }
+    sp = SplitDst{c->A01.ia, c->A10.ia, c->A11.ia, c->A01.a, c->A10.a, c->A11.a};
+  }
   // Mp pattern
   mp_len_kernel<<<nblk(L.npn), 256, 0, st>>>(L, len64); KERNEL_OK();
   c->Mp.n = c->Mp.m = (int)L.npn;
@@ -614,8 +659,9 @@ int fe_assemble(xsb_ctx c)
     const int64_t ne = nei * nej * nek;
     if (ne <= 0) continue;
     if (ne > 0x7fffffff) return xsb_fail(c, XSB_ERR_SUP, "too many elements per colour");
-    if (nsd == 3) assemble_kernel<3><<<(unsigned)ne, 256, 0, st>>>(L, c->lame, col, dT, c->coeff, c->A.ia, c->A.a, c->Mp.ia, c->Mp.a, c->F);
-    else assemble_kernel<2><<<(unsigned)ne, 128, 0, st>>>(L, c->lame, col, dT, c->coeff, c->A.ia, c->A.a, c->Mp.ia, c->Mp.a, c->F);
+    if (split) assemble_kernel<3, true><<<(unsigned)ne, 256, 0, st>>>(L, c->lame, col, dT, c->coeff, nullptr, nullptr, c->Mp.ia, c->Mp.a, c->F, sp);
+    else if (nsd == 3) assemble_kernel<3, false><<<(unsigned)ne, 256, 0, st>>>(L, c->lame, col, dT, c->coeff, c->A.ia, c->A.a, c->Mp.ia, c->Mp.a, c->F, sp);
+    else assemble_kernel<2, false><<<(unsigned)ne, 128, 0, st>>>(L, c->lame, col, dT, c->coeff, c->A.ia, c->A.a, c->Mp.ia, c->Mp.a, c->F, sp);
     KERNEL_OK();
   }
   // Dirichlet data: index list built on the host (integer logic of ISCreate_BCList), applied on the device
@@ -640,19 +686,31 @@ int fe_assemble(xsb_ctx c)
       CUDA_OK(cudaMemcpyAsync(c->bc_val, val.data(), sizeof(double) * c->nbc, cudaMemcpyHostToDevice, st));
       bc_mark_kernel<<<nblk(c->nbc), 256, 0, st>>>(c->nbc, c->bc_idx, c->bc_val, c->isbc, g); KERNEL_OK();
     }
-    XSB_CHK(spmv_csr(c, c->A, g, Ag));   // rhs_diri uses A before rows/columns are zeroed (:2639)
+    if (!split) {
+      XSB_CHK(spmv_csr(c, c->A, g, Ag));   // rhs_diri uses A before rows/columns are zeroed (:2639)
+    } else {
+      // A_raw g with g_p = 0: velocity rows by the unmasked element kernel, pressure rows by A10 before its columns go
+      bool any = false; for (int t = 0; t < c->nbc; ++t) any = any || val[t] != 0.0;
+      CUDA_OK(cudaMemsetAsync(Ag, 0, sizeof(double) * L.n, st));
+      if (any) { XSB_CHK(mf_a00_apply_raw(c, g, Ag)); XSB_CHK(spmv_csr(c, c->A10, g, Ag + L.nu)); }
+    }
     rhs_bc_kernel<<<nblk(L.n), 256, 0, st>>>(L.n, c->isbc, g, Ag, c->F); KERNEL_OK();
-    zero_rows_cols_kernel<<<nblk(L.n * 32), 256, 0, st>>>(L.n, c->A.ia, c->A.ja, c->A.a, c->isbc); KERNEL_OK();
+    if (!split) { zero_rows_cols_kernel<<<nblk(L.n * 32), 256, 0, st>>>(L.n, c->A.ia, c->A.ja, c->A.a, c->isbc); KERNEL_OK(); }
+    else {
+      zero_split_kernel<<<nblk(L.nu * 32), 256, 0, st>>>(L.nu, 1, c->A01.ia, c->A01.ja, c->A01.a, c->isbc); KERNEL_OK();
+      zero_split_kernel<<<nblk(L.np * 32), 256, 0, st>>>(L.np, 0, c->A10.ia, c->A10.ja, c->A10.a, c->isbc); KERNEL_OK();
+    }
     CUDA_OK(cudaStreamSynchronize(st));
   }
   // sub-blocks: A00 as BAIJ(nsd), A01/A10/A11 as CSR
-  {
+  if (split) {   // shell of the velocity block: sizes and pattern descriptor only (products go through xsb_mf.cu)
+    Baij &B = c->A00; B.nb = (int)L.nun; B.bs = nsd; B.pat = BoxPattern{L.NX, L.NY, L.NZ, 1}; B.nblk = 0;
+  } else {
     a00_len_kernel<<<nblk(L.nun), 256, 0, st>>>(L, len64); KERNEL_OK();
     Baij &B = c->A00; B.nb = (int)L.nun; B.bs = nsd; B.pat = BoxPattern{L.NX, L.NY, L.NZ, 1};
     { int rc = scan_to_ia(c, L.nun, len64, &B.ia, &B.nblk); if (rc) { cudaFree(len64); return rc; } }
     XSB_CHK(dev_alloc(c, &B.ja, (size_t)B.nblk)); XSB_CHK(dev_alloc(c, &B.a, (size_t)B.nblk * nsd * nsd + 2));   // +2: the tile kernel's last 16-byte load may straddle the end
     a00_fill_kernel<<<nblk(L.nun * 32), 256, 0, st>>>(L, c->A.ia, c->A.ja, c->A.a, B.ia, B.ja, B.a); KERNEL_OK();
-    struct { Csr *S; int64_t r0, nr; int pcols; } subs[3] = {{&c->A01, 0, L.nu, 1}, {&c->A10, L.nu, L.np, 0}, {&c->A11, L.nu, L.np, 1}};
     for (auto &s : subs) {
       sub_len_kernel<<<nblk(s.nr), 256, 0, st>>>(L, s.r0, s.nr, s.pcols, len64); KERNEL_OK();
       s.S->n = (int)s.nr; s.S->m = s.pcols ? (int)L.np : (int)L.nu;

@@ -58,6 +58,15 @@ int hess_eig(int n, const double *H, int ldh, double *wr, double *wi)
 // y = A x on the full saddle operator; on slabs: ghost update of x, then the owned velocity and pressure rows
 int op_full_mult(xsb_ctx c, const double *x, double *y)
 {
+  if (c->no_A) {   // operator-free: y_u = A00 x_u (element kernel) + A01 x_p ; y_p = A11 x_p + A10 x_u
+    const Lattice &L = c->lat; Epilogue ep;
+    XSB_CHK(mf_setup(c));
+    XSB_CHK(comm_halo_full(c, const_cast<double *>(x)));
+    XSB_CHK(mf_a00_apply(c, x, y, ep));
+    XSB_CHK(spmv_csr(c, c->A01, x + L.nu, y, c->own_u.off0, c->own_u.len0, y));
+    XSB_CHK(spmv_csr(c, c->A11, x + L.nu, y + L.nu, c->own_p.off0, c->own_p.len0));
+    return spmv_csr(c, c->A10, x, y + L.nu, c->own_p.off0, c->own_p.len0, y + L.nu);
+  }
   if (c->slab.nranks == 1) return spmv_csr(c, c->A, x, y);
   XSB_CHK(comm_halo_full(c, const_cast<double *>(x)));
   XSB_CHK(spmv_csr(c, c->A, x, y, c->own_full.off0, c->own_full.len0));
@@ -173,7 +182,11 @@ static int read_solver_options(xsb_ctx c)
   if (ppc == "bjacobi" || ppc == "ilu") s.p_pc = 0; else if (ppc == "jacobi") s.p_pc = 1;
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_fieldsplit_p_pc_type %s not supported (bjacobi|ilu|jacobi)", ppc.c_str());
   s.time_kernels = o.flag("xsb_time_kernels");
-  s.matrix_free = o.flag("xsb_matrix_free");
+  { const std::string mfv = o.str("xsb_matrix_free", "0");   // flag: fine-level products by the element kernel; "full": A / A00 never stored
+    s.matrix_free = (mfv.empty() || mfv == "1" || mfv == "true" || mfv == "yes" || mfv == "full" || mfv == "2") ? 1 : 0;
+    if (c->no_A && !s.matrix_free) return xsb_fail(c, XSB_ERR_ORDER, "the operator was assembled with -xsb_matrix_free full; the option cannot be dropped before xsb_ksp_setup");
+    if (!c->no_A && (mfv == "full" || mfv == "2")) return xsb_fail(c, XSB_ERR_ORDER, "-xsb_matrix_free full must be set before xsb_assemble"); }
+  if (c->no_A && s.pc_type != 2) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free full supports the -fs (ABF) solver tree only");
   if (s.restart < 1 || s.restart > 60 || s.u_restart < 1 || s.u_restart > 60) return xsb_fail(c, XSB_ERR_ARG, "restart must be in [1,60]");
   // monitor / view flags of the reference's command lines are accepted and handled by the caller
   o.has("saddle_ksp_monitor_short"); o.has("saddle_ksp_converged_reason"); o.has("saddle_ksp_view"); o.has("diagnostics");

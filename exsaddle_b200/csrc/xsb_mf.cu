@@ -295,7 +295,7 @@ __global__ void mf_epilogue_kernel(int64_t n, const unsigned char *__restrict__ 
                                    double *__restrict__ out, Epilogue ep)
 {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = mf_epi(ep, i, isbc[i] ? x[i] : kx[i]);
+    out[i] = mf_epi(ep, i, (isbc && isbc[i]) ? x[i] : kx[i]);
 }
 
 int mf_setup(xsb_ctx c)
@@ -315,8 +315,22 @@ int mf_setup(xsb_ctx c)
   return 0;
 }
 
+static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &ep, const unsigned char *isbc, const unsigned char *bcnode);
 // y = epilogue(A00 x), matrix-free.  x and y must not alias.
-int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep)
+int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep) { return mf_apply_core(c, x, y, ep, c->isbc, c->mf_bcnode); }
+// y = K x with no Dirichlet rows / columns (the operator MatAssemble_Saddle holds before MatZeroRowsColumns, used for rhs_diri)
+int mf_a00_apply_raw(xsb_ctx c, const double *x, double *y)
+{
+  XSB_CHK(mf_setup(c));
+  unsigned char *zero = nullptr; CUDA_OK(cudaMalloc(&zero, (size_t)c->lat.nun));
+  CUDA_OK(cudaMemsetAsync(zero, 0, (size_t)c->lat.nun, c->stream));
+  Epilogue ep; const int keep = c->so.mf_kernel; if (c->so.mf_kernel == 1) c->so.mf_kernel = 3;   // v1 reads the per-dof mask
+  int rc = mf_apply_core(c, x, y, ep, nullptr, zero);
+  c->so.mf_kernel = keep;
+  cudaStreamSynchronize(c->stream); cudaFree(zero);
+  return rc;
+}
+static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &ep, const unsigned char *isbc, const unsigned char *bcnode)
 {
   const Lattice &L = c->lat; cudaStream_t st = c->stream;
   const double detJ = L.hu[0] * L.hu[1] * L.hu[2];
@@ -330,7 +344,7 @@ int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep)
       const int64_t ne = (int64_t)((L.mx - ci + 1) / 2) * ((L.my - cj + 1) / 2) * ((L.mz - ck + 1) / 2);
       if (ne <= 0) continue;
       const int64_t warps = (ne + 2) / 3, blocks = (warps * 32 + 127) / 128;
-      mf_a00_kernel<<<(unsigned)blocks, 128, 0, st>>>(L, col, 1.0 / L.hu[0], 1.0 / L.hu[1], 1.0 / L.hu[2], detJ, eta, c->isbc, x, c->mf_tmp); KERNEL_OK();
+      mf_a00_kernel<<<(unsigned)blocks, 128, 0, st>>>(L, col, 1.0 / L.hu[0], 1.0 / L.hu[1], 1.0 / L.hu[2], detJ, eta, isbc, x, c->mf_tmp); KERNEL_OK();
     }
   } else {
     // optional z-chunks of element layers (-xsb_mf_chunk): the 8 colours run chunk by chunk so a chunk's x / y planes stay in L2
@@ -347,13 +361,13 @@ int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep)
         if (ne <= 0) continue;
         const int64_t warps = (ne + 9) / 10; int64_t blocks = (warps + 3) / 4;
         const int rev = c->so.mf_reverse ? (launch++) & 1 : 0;
-        if (c->so.mf_kernel == 2) mf_a00_kernel_v2<1><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, c->mf_bcnode, x, c->mf_tmp);
-        else mf_a00_kernel_v2<0><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, c->mf_bcnode, x, c->mf_tmp);
+        if (c->so.mf_kernel == 2) mf_a00_kernel_v2<1><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, bcnode, x, c->mf_tmp);
+        else mf_a00_kernel_v2<0><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, bcnode, x, c->mf_tmp);
         KERNEL_OK();
       }
     }
   }
   int64_t nb = (L.nu + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
-  mf_epilogue_kernel<<<(unsigned)nb, 256, 0, st>>>(L.nu, c->isbc, x, c->mf_tmp, y, ep); KERNEL_OK();
+  mf_epilogue_kernel<<<(unsigned)nb, 256, 0, st>>>(L.nu, isbc, x, c->mf_tmp, y, ep); KERNEL_OK();
   return 0;
 }

@@ -177,7 +177,7 @@ static int galerkin_replicate(xsb_ctx c, const Level &F, Level &C)
 {
   const int bs = c->nsd, bs2 = bs * bs; cudaStream_t st = c->stream; const Slab &S = c->slab;
   Level T; T.nx = (F.nx - 1) / 2 + 1; T.ny = (F.ny - 1) / 2 + 1; T.nz = (F.nz - 1) / 2 + 1;
-  XSB_CHK(galerkin(c, F, T));
+  if (c->no_A) XSB_CHK(galerkin_elements(c, T)); else XSB_CHK(galerkin(c, F, T));
   BoxPattern gp{C.nx, C.ny, C.nz, 0};
   const int64_t ncn = (int64_t)C.nx * C.ny * C.nz, pn = (int64_t)C.nx * C.ny;
   int64_t *len = nullptr; CUDA_OK(cudaMalloc(&len, sizeof(int64_t) * (ncn + 1)));
@@ -335,6 +335,10 @@ static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, doubl
 static int level_spmv(xsb_ctx c, const Level &L, const double *x, double *y)
 {
   Epilogue ep;
+  if (c->no_A && &L == &c->lev[c->nlev - 1]) {   // operator-free fine level
+    XSB_CHK(comm_halo_u(c, const_cast<double *>(x)));
+    return mf_a00_apply(c, x, y, ep);
+  }
   if (!L.dist) return spmv_baij(c, L.A, x, y, ep);
   XSB_CHK(comm_halo_u(c, const_cast<double *>(x)));
   const int pn = L.nx * L.ny;
@@ -460,6 +464,7 @@ int mg_setup(xsb_ctx c)
   if (levels < 1 || levels > XSB_MAX_LEVELS) return xsb_fail(c, XSB_ERR_ARG, "-saddle_fieldsplit_u_pc_mg_levels %d out of range", levels);
   c->nlev = levels;
   const Slab &S = c->slab; const bool dist = S.nranks > 1;
+  if (c->no_A && levels < 2) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free full needs at least 2 MG levels (a one-level PCMG is LU of the assembled A00)");
   if (dist && levels < 2) return xsb_fail(c, XSB_ERR_SUP, "the slab partition needs at least 2 MG levels (the coarse levels are replicated)");
   { Level &L = c->lev[levels - 1]; L = Level(); L.nx = Lt.NX; L.ny = Lt.NY; L.nz = Lt.NZ; L.A = c->A00; L.owns_A = false; L.dist = dist; }
   for (int l = levels - 2; l >= 0; --l) {
@@ -467,13 +472,15 @@ int mg_setup(xsb_ctx c)
     int dims[3];
     if (xsb_mg_level_dims(c->nsd, Lt.mx, Lt.my, S.mz_glob, levels, l, dims)) return xsb_fail(c, XSB_ERR_ARG, "mesh %dx%dx%d cannot be coarsened to %d MG levels (DMCoarsen needs (n-1) divisible by 2)", Lt.mx, Lt.my, S.mz_glob, levels);
     C.nx = dims[0]; C.ny = dims[1]; C.nz = dims[2];
-    if (F.dist) XSB_CHK(galerkin_replicate(c, F, C)); else XSB_CHK(galerkin(c, F, C));
+    if (F.dist) XSB_CHK(galerkin_replicate(c, F, C));
+    else if (c->no_A && l == levels - 2) XSB_CHK(galerkin_elements(c, C));
+    else XSB_CHK(galerkin(c, F, C));
   }
   for (int l = 0; l < levels; ++l) {
     Level &L = c->lev[l]; const int64_t n = (int64_t)L.A.nb * L.A.bs;
     XSB_CHK(dev_alloc(c, &L.x, (size_t)n)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)n));
     XSB_CHK(dev_alloc(c, &L.w0, (size_t)n)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)n)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
-    XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
+    if (c->no_A && l == levels - 1) XSB_CHK(mf_diag_inv(c, L.idiag)); else XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
   }
   // large replicated levels: split the rows of every smoother / residual product over the ranks (-xsb_rowpart_min_nodes)
   if (dist) {

@@ -24,7 +24,7 @@ __device__ __forceinline__ double warp_sum(double v)
 // ------------------------------------------------------------------ K1: CSR
 template <int UNROLL>
 __global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t row0, int64_t n, const int *__restrict__ ia, const int *__restrict__ ja,
-                                                       const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y)
+                                                       const double *__restrict__ a, const double *__restrict__ x, double *y, const double *yadd /* may alias y */)
 {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -41,11 +41,11 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t row0, int64_t n, 
     }
     for (; k < k1; k += 32) acc += ld_stream(a + k) * __ldg(x + ld_stream(ja + k));
     acc = warp_sum(acc);
-    if (lane == 0) y[row] = acc;
+    if (lane == 0) y[row] = yadd ? acc + yadd[row] : acc;
   }
 }
 
-int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0, int64_t nrows)
+int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0, int64_t nrows, const double *yadd)
 {
   if (nrows < 0) nrows = A.n - row0;
   if (nrows <= 0) return XSB_OK;
@@ -53,7 +53,7 @@ int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0, 
   int64_t blocks = (warps * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;   // persistent-style grid: 148 SMs x 8 resident CTAs x 16 waves
   if (blocks > cap) blocks = cap;
-  spmv_csr_kernel<8><<<(unsigned)blocks, tpb, 0, c->stream>>>(row0, nrows, A.ia, A.ja, A.a, x, y); KERNEL_OK();
+  spmv_csr_kernel<8><<<(unsigned)blocks, tpb, 0, c->stream>>>(row0, nrows, A.ia, A.ja, A.a, x, y, yadd); KERNEL_OK();
   return XSB_OK;
 }
 

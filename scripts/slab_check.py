@@ -58,7 +58,9 @@ ok = True
 for name, opts, ptype in (("jacobi_gmres", "-model 1 -mx %d -eta1 10 -saddle_pc_type jacobi -saddle_ksp_max_it 25" % MX, "jacobi"),
                           ("abf_pjacobi", ABF + "-saddle_fieldsplit_p_pc_type jacobi -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
                           ("abf_bjacobi_ilu", ABF + "-saddle_fieldsplit_p_pc_type bjacobi -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf_ilu"),
-                          ("abf_pjacobi_mf", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_matrix_free -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf")):
+                          ("abf_pjacobi_mf", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_matrix_free -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
+                          ("abf_pjacobi_mffull", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_matrix_free full -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
+                          ("abf_pjacobi_rowpart", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_rowpart_min_nodes 100 -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf")):
     gd = make(opts, True)
     part = gd.partition()
     g1 = make(opts, False)          # every rank keeps a one-GPU copy as the reference (small problem)

@@ -293,3 +293,48 @@ def test_matrix_free_solve_matches_assembled_solve():
     assert np.max(np.abs(ha - hm)) <= 1e-10 * ha[0]
     assert np.linalg.norm(xa - xm) <= 1e-7 * np.linalg.norm(xa)
     ga.close(); gm.close()
+
+
+# ------------------------------------------------------------------ operator-free mode (-xsb_matrix_free full): A / A00 never stored
+FULL_CASES = [("stokes_8_l3_contrast", False, "-model 6 -mx 8 -eta1 1e4", 3), ("stokes_noncubic_l2", False, "-model 1 -mx 4 -my 6 -mz 2", 2),
+              ("stokes_pseudoice_l3", False, "-model 11 -size_x 0.1 -mx 6", 3), ("lame_compression2_l2", True, "-model 12 -mx 4 -mu1 10 -lambda1 100", 2)]
+
+
+@pytest.mark.parametrize("name,lame,opts,levels", FULL_CASES, ids=[c[0] for c in FULL_CASES])
+def test_operator_free_mode_matches_oracle_and_assembled_path(name, lame, opts, levels):
+    full = "%s %s -saddle_fieldsplit_u_pc_mg_levels %d -saddle_ksp_rtol 1e-8" % (ABF, opts, levels)
+    g = X.ExSaddle(full + " -xsb_matrix_free full", nsd=3, lame=lame).assemble().ksp_setup()
+    ga = X.ExSaddle(full, nsd=3, lame=lame).assemble().ksp_setup()
+    o = O.Problem(full, nsd=3, lame=lame)
+    res = o.pc_setup()
+    # sizes, RHS (incl. the Dirichlet lifting through the unmasked element kernel), operator apply
+    assert (g.n, g.nu, g.np_, g.nnz) == (o.n, o.nu, o.np_, o.nnz)
+    assert _relerr(g.rhs(), o.F()) <= 1e-13
+    rng = np.random.default_rng(3)
+    for x in (np.sin(0.37 * np.arange(o.n)) + 0.1, rng.standard_normal(o.n)):
+        yo = o.mult(x)
+        assert np.linalg.norm(g.mat_mult(X.MAT_A, x) - yo) <= 1e-12 * np.linalg.norm(yo)
+    for which in (X.MAT_A01, X.MAT_A10, X.MAT_A11, X.MAT_MP):
+        (ia, ja, a, shape), (ia2, ja2, a2, shape2) = g.mat_csr(which), ga.mat_csr(which)
+        assert shape == shape2 and np.array_equal(ia, ia2) and np.array_equal(ja, ja2) and np.array_equal(a, a2)
+    with pytest.raises(X.XsbError):
+        g.mat_csr(X.MAT_A)
+    # element-wise Galerkin product and everything below it; Jacobi diagonal through the Chebyshev bounds
+    for l in range(levels - 1):
+        ia, ja, a, shape = g.mat_csr(X.MAT_MG_LEVEL0 + l)
+        L = o.mg_level(l)
+        assert shape == L.shape and np.array_equal(ia, L.ia) and np.array_equal(ja, L.ja)
+        assert _relerr(a, L.a) <= 1e-12
+    for l in range(1, levels):
+        emin_est, emax_est, emin, emax = g.chebyshev(l)
+        assert abs(emax_est - res.cheb_emax_est[l]) <= 1e-9 * emax_est
+    # the solve: same iteration counts as the oracle and the assembled GPU path, same history
+    x = g.solve(); xa = ga.solve(); xo, r = o.solve()
+    assert g.iterations() == ga.iterations() == (r.its, r.reason)
+    assert g.inner_iterations() == ga.inner_iterations() == list(r.inner_its[:r.n_inner])
+    h = g.history(); ho = np.array(r.hist[:r.nhist])
+    assert np.max(np.abs(h - ho)) <= 1e-10 * ho[0]
+    assert np.linalg.norm(x - xo) <= 1e-7 * np.linalg.norm(xo)
+    F = o.F()
+    assert np.linalg.norm(F - o.mult(x)) <= 1.6e-8 * np.linalg.norm(F)
+    g.close(); ga.close()
