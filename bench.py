@@ -6,7 +6,13 @@ Metric (BASELINE.json): Stokes KSP solve time to rtol 1e-8 (s) -- FGMRES + field
 A "step" is one KSPSolve of the assembled system (zero initial guess, second-solve protocol of exSaddle.c:569-599:
 set-up is outside the timed region).  Inputs (A00 alone is 10.4 GB at 64^3) are far larger than the 126 MB L2.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--mx 64] [--eta1 1e6] [--levels 6] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mx 64] [--eta1 1e6] [--levels 6] [--path assembled|operator-free] [--impl reference]
+
+--path assembled (default): A is the reference's MATAIJ layout, A00 / Galerkin levels BAIJ(3); the roofline is the HBM
+roofline of the fine-level A00 SpMV.  The same solve with the operator-free fine level (-xsb_matrix_free full: neither A
+nor A00 stored, sum-factorised Q2 element kernel) is timed beside it and reported under "matrix_free".
+--path operator-free: the operator-free solve is the timed step (the only path at 128^3 below 8 GPUs: nnz(A) = 1.13e10
+does not fit 32-bit indices); the roofline is then the FP64 issue roofline of the element kernel (measured FMA peak).
 
 N > 1 (torchrun): the SAME problem is cut into z-slabs, one per GPU (strong scaling): NCCL halo exchange in front of
 every operator apply, NCCL all-reduce behind every Krylov reduction; value = solve time, max over ranks.
@@ -32,6 +38,42 @@ ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iterations.json")
 
 def workload_options(a):
     return "%s -saddle_fieldsplit_u_pc_mg_levels %d -model 6 -mx %d -eta0 1 -eta1 %g -saddle_ksp_rtol 1e-8" % (ABF, a.levels, a.mx, a.eta1)
+
+
+# measured once per kernel change with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
+NCU_TRAFFIC = {("spmv_baij", 64, 1): 10.81e9, ("mf_a00", 64, 1): 8 * 71.8e6}
+FP64_PEAK_TFLOPS = 36.72      # scripts/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak.json): 63.1 DFMA/clk/SM at 1965 MHz
+MF_FLOP_PER_ELEMENT = 7140.0  # FP64 flops the element kernel executes per element: 3 lanes x (927 DFMA x 2 + 418 DMUL + 108 DADD), cuobjdump -sass
+
+
+def timed_solves(g, torch, xdev, steps, barrier):
+    """K solves, device-resident RHS, CUDA events on the handle's own stream; returns (ms, counters summed over the steps)."""
+    stream = torch.cuda.ExternalStream(g.stream(), device=xdev.device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0; a00_ns = []; modes = [0, 0, 0, 0]; n_a00 = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            g.solve_dev(0, xdev.data_ptr())
+            c = g.counters(); launches += c["launches"]; a00_ns.append(c["a00_avg_ns"]); n_a00 += c["a00_spmv"]
+            modes = [u + v for u, v in zip(modes, c["a00_by_mode"])]
+        ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1), launches, sum(a00_ns) / len(a00_ns), n_a00, modes
+
+
+def timed_e2e(g, X, torch, device, F_host, x_host, steps, barrier):
+    """K solves through the host-pointer C-ABI call: pinned host RHS -> device, solution -> host inside the timed region."""
+    stream = torch.cuda.ExternalStream(g.stream(), device=device)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            g._chk(g.L.xsb_ksp_solve(g.h, X.api._dp(F_host.numpy()), X.api._dp(x_host.numpy())))
+        e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1)
 
 
 def workload_name(a):
@@ -142,14 +184,18 @@ def main():
     ap.add_argument("--sample-outer", dest="sample_outer", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matrix-free", dest="no_matrix_free", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "assembled", "operator-free"])
     a = ap.parse_args()
+    if a.path == "auto":   # the assembled AIJ operator needs nnz(A) per rank < 2^31 (32-bit PetscInt)
+        a.path = "assembled" if 5420.0 * a.mx ** 3 / max(1, a.gpus) < 2.0e9 else "operator-free"
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
-    cfg = {"workload": workload_name(a), "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
-           "parallelism": "1 GPU" if world == 1 else "one problem, z-slab partition over %d GPUs (one process per GPU): NCCL send/recv halo exchange before every operator apply, NCCL all-reduce for Krylov dot products; fine MG level distributed, coarse levels replicated, ILU(0) per rank (bjacobi)" % world,
-           "l2": "inputs (A00 BAIJ 10.4 GB at 64^3) far exceed the 126 MB L2; no flush needed",
+    cfg = {"workload": workload_name(a), "path": a.path, "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
+           "parallelism": "1 GPU" if world == 1 else "one problem, z-slab partition over %d GPUs (one process per GPU): NCCL send/recv halo exchange before every operator apply, NCCL all-reduce for Krylov dot products; fine MG level distributed, coarse levels replicated (products of the large ones row-partitioned + all-gathered), ILU(0) per rank (bjacobi)" % world,
+           "l2": ("inputs (A00 BAIJ 10.4 GB at 64^3) far exceed the 126 MB L2; no flush needed" if a.path == "assembled" else
+                  "x, y, viscosity and the first Galerkin level (>= 0.7 GB at 64^3) exceed the 126 MB L2; no flush needed"),
            "options": workload_options(a)}
 
     if a.impl == "reference":
@@ -174,20 +220,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    g = X.ExSaddle(workload_options(a) + " -xsb_time_kernels", nsd=3, device=local)
-    if world > 1:   # one problem, z-slabs over the ranks: NCCL communicator inside the library, id shipped by torch.distributed
-        uid = [X.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        g.comm_init(uid[0], rank, world)
-    t0 = time.time(); g.assemble(); t_asm = time.time() - t0
-    part = g.partition()
-    own_frac = part["u_len"] / float(g.nu)   # share of the local lattice this rank owns (ghost layers excluded)
-    t0 = time.time(); g.ksp_setup(); t_setup = time.time() - t0
-    n = g.n
-    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local))
-    xdev = torch.empty(n, dtype=torch.float64, device="cuda")
-    F_host = torch.from_numpy(g.rhs()).pin_memory()
-    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    def make(extra):
+        h = X.ExSaddle(workload_options(a) + " -xsb_time_kernels" + extra, nsd=3, device=local)
+        if world > 1:   # one problem, z-slabs over the ranks: NCCL communicator inside the library, id shipped by torch.distributed
+            uid = [X.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            h.comm_init(uid[0], rank, world)
+        return h
 
     def barrier():
         torch.cuda.synchronize()
@@ -195,71 +234,59 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    opfree = a.path == "operator-free"
+    g = make(" -xsb_matrix_free full" if opfree else "")
+    t0 = time.time(); g.assemble(); t_asm = time.time() - t0
+    part = g.partition()
+    own_frac = part["u_len"] / float(g.nu)   # share of the local lattice this rank owns (ghost layers excluded)
+    t0 = time.time(); g.ksp_setup(); t_setup = time.time() - t0
+    n = g.n
+    xdev = torch.empty(n, dtype=torch.float64, device="cuda")
+    F_host = torch.from_numpy(g.rhs()).pin_memory()
+    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+
     # ---- device-resident timing: K solves, CUDA events on the launching stream
     for _ in range(warmup):
         g.solve_dev(0, xdev.data_ptr())
     barrier()
     sampler = ClockSampler(local); sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0; a00_ns = []; a00_modes = [0, 0, 0, 0]; n_a00 = 0
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for _ in range(a.steps):
-            g.solve_dev(0, xdev.data_ptr())
-            c = g.counters(); launches += c["launches"]; a00_ns.append(c["a00_avg_ns"]); n_a00 += c["a00_spmv"]
-            a00_modes = [u + v for u, v in zip(a00_modes, c["a00_by_mode"])]
-        ev1.record(stream)
-    barrier()
+    ms, launches, avg_ns, n_a00, a00_modes = timed_solves(g, torch, xdev, a.steps, barrier)
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
     its, reason = g.iterations()
     inner = g.inner_iterations()
     hist = g.history()
     # ---- end to end through the host-pointer C-ABI call: pinned host RHS -> device, solution -> host, every step
-    barrier()
-    with torch.cuda.stream(stream):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(a.steps):
-            g._chk(g.L.xsb_ksp_solve(g.h, X.api._dp(F_host.numpy()), X.api._dp(x_host.numpy())))
-        e1.record(stream)
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms_e2e = timed_e2e(g, X, torch, xdev.device, F_host, x_host, a.steps, barrier)
+    ms, ms_e2e = allmax([ms, ms_e2e])
     sec_per_solve = ms / 1e3 / a.steps
     e2e_per_solve = ms_e2e / 1e3 / a.steps
 
-    # ---- same solve with the fine-level A00 products done matrix-free (K4): reported beside the assembled path
-    mf = None
-    if not a.no_matrix_free:
-        g.set_option("-xsb_matrix_free"); g.ksp_setup()
-        for _ in range(2):
-            g.solve_dev(0, xdev.data_ptr())
-        barrier()
-        with torch.cuda.stream(stream):
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record(stream)
-            for _ in range(a.steps):
-                g.solve_dev(0, xdev.data_ptr())
-            f1.record(stream)
-        barrier()
-        cm = g.counters(); its_mf, reason_mf = g.iterations()
-        tm = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        nel = a.mx ** 3
-        mf = {"value": float(tm[0]) / 1e3 / a.steps, "unit": "s", "outer_its": its_mf, "reason": reason_mf,
-              "a00_apply_avg_us": cm["a00_avg_ns"] / 1e3, "a00_apply_gflops": (2 * 5900.0 * nel) / max(cm["a00_avg_ns"], 1),
-              "note": "fine-level A00 products by the sum-factorised Q2 element kernel (FP64-issue bound: ~5.9 kFMA/element, 16 B/dof of HBM traffic); coarse levels and the outer MatMult stay assembled"}
+    def fp64_roofline(avg_apply_ns, n_applies, step_seconds):
+        flops = MF_FLOP_PER_ELEMENT * nel_local   # every element of the local lattice (ghost layers included on slabs)
+        ach = flops / max(avg_apply_ns, 1) / 1e3   # TFLOP/s
+        tr = NCU_TRAFFIC.get(("mf_a00", a.mx, world))
+        return {"bound": "fp64", "kernel": "mf_a00_kernel_v2 x 8 colours + epilogue (sum-factorised Q2 element apply of A00)", "achieved": ach,
+                "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "traffic": tr,
+                "peak_source": "measured FP64 FMA micro-kernel (scripts/fp64_peak.cu, profiles/r01_fp64_peak.json); not in MEASURED_PEAKS.json",
+                "flops_per_launch": flops, "avg_launch_us": avg_apply_ns / 1e3, "launches_timed": n_applies,
+                "share_of_step": (n_applies * avg_apply_ns * 1e-9) / step_seconds,
+                "hbm_view": {"algorithmic_bytes": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world,
+                             "achieved_GBps": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world / max(avg_apply_ns, 1)}}
 
-    # collective on slabs (halo exchange inside): every rank runs it
+    # ---- full-A MatMult micro-measure (collective on slabs: every rank runs it): 10 warm-up + 30 timed applies.
+    # Assembled path: the reference's MATAIJ layout; operator-free path: element kernel + A01 / A10 / A11 CSR products.
     a_info = g.mat_info(X.MAT_A)
-    # full-A AIJ MatMult micro-measure (the reference's MATAIJ layout): 20 warm-up + 50 timed applies
+    a00_info = g.mat_info(X.MAT_A00)
+    nel_local = g.nel
     xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
     yout = torch.empty_like(xin)
+    stream = torch.cuda.ExternalStream(g.stream(), device=xdev.device)
     with torch.cuda.stream(stream):
         for _ in range(10):
             g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
@@ -270,20 +297,43 @@ def main():
         m1.record(stream)
     torch.cuda.synchronize()
     aij_ms = m0.elapsed_time(m1) / 30
+    del xin, yout
+
+    # ---- assembled path: the same solve with the operator-free fine level (K4), reported beside it
+    mf = None
+    if not opfree and not a.no_matrix_free:
+        g.close(); g = None
+        torch.cuda.empty_cache()
+        g = make(" -xsb_matrix_free full")
+        g.assemble(); g.ksp_setup()
+        for _ in range(2):
+            g.solve_dev(0, xdev.data_ptr())
+        barrier()
+        ms_mf, l_mf, ns_mf, n_mf, _ = timed_solves(g, torch, xdev, a.steps, barrier)
+        ms_mf_e2e = timed_e2e(g, X, torch, xdev.device, F_host, x_host, a.steps, barrier)
+        its_mf, reason_mf = g.iterations()
+        ms_mf, ms_mf_e2e = allmax([ms_mf, ms_mf_e2e])
+        mf = {"value": ms_mf / 1e3 / a.steps, "unit": "s", "e2e": ms_mf_e2e / 1e3 / a.steps, "outer_its": its_mf, "reason": reason_mf,
+              "inner_gcr_its": int(sum(g.inner_iterations())), "gpu_launches": l_mf,
+              "roofline": fp64_roofline(ns_mf, n_mf, ms_mf / 1e3),
+              "note": "-xsb_matrix_free full: neither A nor A00 stored; fine-level A00 products (smoother, GCR, outer MatMult) by the sum-factorised Q2 "
+                      "element kernel, first Galerkin level assembled element by element; identical iteration counts (tests/test_gpu_parity.py)"}
 
     if rank == 0:
         peak, peak_src = peaks()
-        info = g.mat_info(X.MAT_A00)
-        bytes_launch = a00_bytes(info, a00_modes) * own_frac   # owned rows only are streamed (own_frac = 1 on one GPU)
-        avg_ns = sum(a00_ns) / len(a00_ns)
-        achieved = bytes_launch / avg_ns if avg_ns else 0.0   # B/ns = GB/s
-        aij_bytes = (12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]) * own_frac
-        roof = {"bound": "hbm", "kernel": "spmv_baij_kernel<3> (fine-level A00 with fused residual/Chebyshev epilogue)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
-                "launches_timed": n_a00, "share_of_step": (n_a00 * avg_ns * 1e-9) / (sec_per_solve * a.steps),
-                "aij_matmult": {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)", "ms": aij_ms, "bytes": aij_bytes,
-                                "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak}}
+        if opfree:
+            roof = fp64_roofline(avg_ns, n_a00, sec_per_solve * a.steps)
+            roof["full_matmult"] = {"kernel": "element kernel (A00) + spmv_csr_kernel on A01 / A10 / A11", "ms": aij_ms}
+        else:
+            bytes_launch = a00_bytes(a00_info, a00_modes) * own_frac   # owned rows only are streamed (own_frac = 1 on one GPU)
+            achieved = bytes_launch / avg_ns if avg_ns else 0.0   # B/ns = GB/s
+            aij_bytes = (12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]) * own_frac
+            roof = {"bound": "hbm", "kernel": "spmv_baij_kernel<3> (fine-level A00 with fused residual/Chebyshev epilogue)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(("spmv_baij", a.mx, world)),
+                    "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
+                    "launches_timed": n_a00, "share_of_step": (n_a00 * avg_ns * 1e-9) / (sec_per_solve * a.steps),
+                    "aij_matmult": {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)", "ms": aij_ms, "bytes": aij_bytes,
+                                    "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak}}
         os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
         try:
             d = json.load(open(ITERS_FILE)) if os.path.exists(ITERS_FILE) else {}
@@ -311,7 +361,8 @@ def main():
                 "e2e": {"value": e2e_per_solve, "unit": "s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))
-    g.close()
+    if g is not None:
+        g.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -45,10 +45,36 @@ __global__ void __launch_bounds__(256) spmv_csr_kernel(int64_t row0, int64_t n, 
   }
 }
 
+// Short rows (A01: 8..27 entries per velocity row): LPR lanes per row, 32 / LPR rows per warp, so a load instruction
+// still covers 32 consecutive entries of consecutive rows instead of one partly filled row.
+template <int LPR>
+__global__ void __launch_bounds__(256) spmv_csr_short_kernel(int64_t row0, int64_t n, const int *__restrict__ ia, const int *__restrict__ ja,
+                                                             const double *__restrict__ a, const double *__restrict__ x, double *y, const double *yadd /* may alias y */)
+{
+  constexpr int GPW = 32 / LPR;   // rows per warp
+  const int sub = threadIdx.x & (LPR - 1), gw = (threadIdx.x & 31) / LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t rb = warp * GPW; rb < n; rb += nwarps * GPW) {   // trip count is uniform per warp: the shuffles below are full-mask
+    const int64_t r = rb + gw, row = row0 + r; const bool ok = r < n;
+    const int k0 = ok ? ia[row] : 0, k1 = ok ? ia[row + 1] : 0;
+    double acc = 0.0;
+    for (int k = k0 + sub; k < k1; k += LPR) acc += ld_stream(a + k) * __ldg(x + ld_stream(ja + k));
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, LPR);
+    if (ok && sub == 0) y[row] = yadd ? acc + yadd[row] : acc;
+  }
+}
+
 int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0, int64_t nrows, const double *yadd)
 {
   if (nrows < 0) nrows = A.n - row0;
   if (nrows <= 0) return XSB_OK;
+  if (A.nnz < 40 * (int64_t)A.n) {   // short rows
+    const int tpb = 256; int64_t blocks = (nrows * 8 + tpb - 1) / tpb;
+    const int64_t cap = 148LL * 8 * 32; if (blocks > cap) blocks = cap;
+    spmv_csr_short_kernel<8><<<(unsigned)blocks, tpb, 0, c->stream>>>(row0, nrows, A.ia, A.ja, A.a, x, y, yadd); KERNEL_OK();
+    return XSB_OK;
+  }
   const int64_t warps = nrows; const int tpb = 256;
   int64_t blocks = (warps * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;   // persistent-style grid: 148 SMs x 8 resident CTAs x 16 waves
