@@ -70,6 +70,8 @@ def lib():
         L.xo_solver_init.argtypes = [C.POINTER(Solver)]
         L.xo_solver_abf.argtypes = [C.POINTER(Solver)]
         L.xo_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+        L.xo_create_nodal.argtypes = [C.POINTER(Params), dp, C.POINTER(vp)]
+        L.xo_coeff_nodal.argtypes = [vp]; L.xo_coeff_nodal.restype = dp
         L.xo_destroy.argtypes = [vp]
         L.xo_banner.argtypes = [vp]; L.xo_banner.restype = C.c_char_p
         L.xo_error.argtypes = [vp]; L.xo_error.restype = C.c_char_p
@@ -239,13 +241,17 @@ class CSR:
 class Problem:
     """One exSaddle run: Problem('-model 0 -mx 4 ...', nsd=2)."""
 
-    def __init__(self, opts, nsd=3, lame=False, options_file_dir=None):
+    def __init__(self, opts, nsd=3, lame=False, options_file_dir=None, nodal=None):
         self.L = lib()
         self.o = parse_options(opts, options_file_dir) if not isinstance(opts, dict) else dict(opts)
         self.nsd, self.lame = nsd, lame
         self.params = make_params(self.o, nsd, lame)
         self.h = C.c_void_p()
-        rc = self.L.xo_create(C.byref(self.params), C.byref(self.h))
+        if nodal is None:
+            rc = self.L.xo_create(C.byref(self.params), C.byref(self.h))
+        else:   # coarse level of the -mg hierarchy: coefficients interpolated from nodal Q1 fields (npn x 6)
+            nodal = np.ascontiguousarray(nodal, dtype=np.float64)
+            rc = self.L.xo_create_nodal(C.byref(self.params), _dp(nodal), C.byref(self.h))
         if rc:
             msg = self.L.xo_error(self.h).decode()
             self.L.xo_destroy(self.h); self.h = None
@@ -254,6 +260,10 @@ class Problem:
         self.L.xo_sizes(self.h, sz)
         (self.n, self.nu, self.np_, self.nnz, self.prealloc, self.nel, self.nbc, self.mnnz) = [int(v) for v in sz]
         self.banner = self.L.xo_banner(self.h).decode()
+
+    def coeff_nodal(self):
+        """nodal Q1 coefficient fields, (p nodes, 6 slots: eta|mu, Fu0, Fu1, Fu2, Fp, lambda)"""
+        return self._arr(self.L.xo_coeff_nodal(self.h), self.np_ * 6, np.float64).reshape(self.np_, 6).copy()
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -90,6 +90,9 @@ void xo_solver_abf(xo_solver *s); /* abf.opts */
 
 /* Build everything exSaddle.c:215-283 builds: mesh, coefficients, A (BCs imposed), F, Mpscaled. */
 int  xo_create(const xo_params *prm, xo_problem **out);
+/* coarse level of the monolithic -mg hierarchy: coefficients from nodal Q1 fields (npn x 6, node-major) */
+int  xo_create_nodal(const xo_params *prm, const double *nodal, xo_problem **out);
+const double *xo_coeff_nodal(const xo_problem *p); /* npn x 6 nodal Q1 coefficient fields (after the projection) */
 void xo_destroy(xo_problem *p);
 const char *xo_banner(const xo_problem *p); /* BC / model banner lines (models.c PetscPrintf) */
 const char *xo_error(const xo_problem *p);

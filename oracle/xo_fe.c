@@ -437,6 +437,26 @@ static void define_qp_properties(xo_problem *P)
   }
 }
 
+/* nodal Q1 coefficient fields -> quadrature points (femixedspace.c:2036-2083 fine level, :2168-2215 coarse levels) */
+static void interp_nodal_to_qp(xo_problem *P)
+{
+  const int nbp = P->nbp, nqp = P->nqp;
+  const double *nodal = P->coeff_nodal;
+  int64_t e;
+#pragma omp parallel for schedule(static)
+  for (e = 0; e < P->nel; ++e) {
+    int i, q, s;
+    for (q = 0; q < nqp; ++q) {
+      double *c = &P->coeff[((size_t)e * nqp + q) * XO_NSLOT];
+      for (s = 0; s < XO_NSLOT; ++s) {
+        double v = 0.0;
+        for (i = 0; i < nbp; ++i) v += P->Np[q][i] * nodal[(size_t)P->p_map[nbp * e + i] * XO_NSLOT + s];
+        c[s] = v;
+      }
+    }
+  }
+}
+
 /* FEMixedSpaceDefineQPwiseProperties_Q1Projection, fine level (femixedspace.c:1976-2083) */
 static void q1_projection(xo_problem *P)
 {
@@ -462,20 +482,9 @@ static void q1_projection(xo_problem *P)
     int64_t nd; int s;
     for (nd = 0; nd < P->npn; ++nd) for (s = 0; s < XO_NSLOT; ++s) nodal[(size_t)nd * XO_NSLOT + s] /= scale[nd];   /* :2017 */
   }
-#pragma omp parallel for schedule(static)
-  for (e = 0; e < P->nel; ++e) {   /* interpolate back to the quadrature points (:2036-2083) */
-    int i, q, s;
-    for (q = 0; q < nqp; ++q) {
-      double *c = &P->coeff[((size_t)e * nqp + q) * XO_NSLOT];
-      for (s = 0; s < XO_NSLOT; ++s) {
-        double v = 0.0;
-        for (i = 0; i < nbp; ++i) v += P->Np[q][i] * nodal[(size_t)P->p_map[nbp * e + i] * XO_NSLOT + s];
-        c[s] = v;
-      }
-    }
-  }
   P->coeff_nodal = nodal;
   free(scale);
+  interp_nodal_to_qp(P);
 }
 
 /* ------------------------------------------------------------ BC lists */
@@ -844,6 +853,31 @@ int xo_create(const xo_params *prm, xo_problem **out)
   P->create_seconds = xo_wtime() - t0;
   return 0;
 }
+
+/* A coarse level of the monolithic -mg hierarchy (exSaddle.c:215-270): same model / BCs on a coarser mesh, with the
+   quadrature-point coefficients interpolated from the given nodal Q1 fields (restricted from the finer level,
+   femixedspace.c:2139-2215) instead of evaluated from the model.  nodal: npn x XO_NSLOT, node-major. */
+int xo_create_nodal(const xo_params *prm, const double *nodal, xo_problem **out)
+{
+  xo_problem *P = (xo_problem *)calloc(1, sizeof(xo_problem));
+  double t0 = xo_wtime();
+  *out = P;
+  P->prm = *prm;
+  if (resolve_params(P)) return 1;
+  if (build_mesh(P)) return 1;
+  build_tables(P);
+  build_bc(P);
+  P->coeff = (double *)calloc((size_t)P->nel * P->nqp * XO_NSLOT, sizeof(double));
+  P->coeff_nodal = (double *)malloc((size_t)P->npn * XO_NSLOT * sizeof(double));
+  memcpy(P->coeff_nodal, nodal, (size_t)P->npn * XO_NSLOT * sizeof(double));
+  interp_nodal_to_qp(P);
+  if (build_pattern(P)) return 1;
+  assemble(P);
+  impose_bc(P, P->n <= 200000);
+  P->create_seconds = xo_wtime() - t0;
+  return 0;
+}
+const double *xo_coeff_nodal(const xo_problem *P) { return P->coeff_nodal; }
 
 void xo_destroy(xo_problem *P)
 {

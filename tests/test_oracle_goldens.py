@@ -256,3 +256,35 @@ def test_galerkin_and_transfers_vs_scipy(kat):
     xc = rng.standard_normal(P.shape[1]); xf = rng.standard_normal(P.shape[0])
     assert np.allclose(p.prolong_add(0, xc, xf.copy()), xf + P @ xc, rtol=1e-13)
     assert np.allclose(p.restrict(0, xf, P.shape[1]), P.T @ xf, rtol=1e-13)
+
+
+# ---- monolithic -mg path: rediscretised levels, GMRES/Jacobi smoothers, LU coarse solve ----
+def _short(v):
+    return "%g" % v if v > 1e-9 else ("%5.3e" % v if v > 1e-11 else "< 1.e-11")   # KSPMonitorDefaultShort
+
+
+@pytest.mark.parametrize("name", ["exSaddle3d_mg_1", "exSaddle2d_mg_1", "exSaddle2d_lame_mg_1", "exSaddle3d_lame_mg_1"])
+def test_monolithic_mg_history_and_diagnostics_match_golden(kat, name):
+    from oracle.oracle_mg import MonolithicMG
+    c = kat[name]
+    M = MonolithicMG(c["options"], nsd=c["nsd"], lame=c["lame"])
+    x, its, reason, hist = M.solve()
+    assert reason == 2 and its == len(c["residuals"]) - 1
+    assert [_short(v) for v in hist] == c["residuals_text"]          # every printed digit of every iteration
+    got = M.fine.diagnostics_text(x)
+    assert [g.rstrip() for g in got] == [s.rstrip() for s in c["diagnostics"]]
+    assert M.fine.banner.rstrip("\n").split("\n") == c["banner"]
+
+
+def test_monolithic_mg_two_rank_goldens_equal_the_one_rank_ones(kat):
+    # the reference's -n 2 runs print the same histories: nothing in the path depends on the partition
+    for a, b in (("exSaddle3d_mg_1", "exSaddle3d_mg_2"), ("exSaddle2d_mg_1", "exSaddle2d_mg_2")):
+        assert kat[a]["residuals_text"] == kat[b]["residuals_text"]
+
+
+def test_monolithic_mg_option_errors():
+    from oracle.oracle_mg import MonolithicMG
+    with pytest.raises(ValueError):
+        MonolithicMG("-mx 6 -mg -nlevels 3 -saddle_ksp_type fgmres -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi", nsd=3)   # 6 % 4 != 0 (exSaddle.c:220)
+    with pytest.raises(ValueError):
+        MonolithicMG("-mx 8 -mg -nlevels 1 -saddle_ksp_type fgmres -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi", nsd=3)   # exSaddle.c:209
