@@ -139,7 +139,7 @@ struct Model {   // resolved model parameters (models.c static option blocks)
 
 struct SolverOpts {
   int ksp_type = 0;      // 0 gmres 1 fgmres
-  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf)
+  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf) 3 monolithic PCMG (-mg)
   int right = 0;
   double rtol = 1e-5, atol = 1e-50, dtol = 1e4; int max_it = 10000, restart = 30;
   double u_rtol = 1e-5; int u_max_it = 10000, u_restart = 30;
@@ -193,6 +193,8 @@ struct xsb_ctx_s {
   Ranges own_full, own_u, own_p;            // owned entries of [u|p], u and p vectors on the local lattice
   std::vector<void *> allocs;   // every device allocation, for xsb_reset
   void *fe_tables = nullptr;    // FeTables on the device
+  void *mmg = nullptr;          // monolithic -mg hierarchy (xsb_mmg.cu)
+  const double *nodal_in = nullptr;   // coarse -mg level: nodal Q1 coefficient fields [slot][p-node] to use instead of the model
 };
 
 int xsb_fail(xsb_ctx c, int code, const char *fmt, ...);
@@ -256,6 +258,12 @@ int mg_restrict(xsb_ctx c, const Level &F, const Level &C, const double *rf, dou
 int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, double *xf);
 int baij_to_csr_host(xsb_ctx c, const Baij &A, int32_t *ia, int32_t *ja, double *a);
 int baij_diag_inv(xsb_ctx c, const Baij &A, double *idiag);
+int mg_restrict_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny, int cnz, const double *rf, double *bc);   // pressure lattice
+int mg_prolong_add_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny, const double *xc, double *xf);
+// ---- xsb_mmg.cu (monolithic -mg)
+int mmg_setup(xsb_ctx c);
+int mmg_apply(xsb_ctx c, const double *r, double *z);
+void mmg_free(xsb_ctx c);
 // ---- xsb_ilu.cu
 int ilu_setup(xsb_ctx c);
 int ilu_apply(xsb_ctx c, const double *b, double *x);

@@ -606,8 +606,12 @@ int fe_assemble(xsb_ctx c)
   const int64_t nq = L.nel * nqp;
   XSB_CHK(dev_alloc(c, &c->coeff, (size_t)XSB_NSLOT * nq));
   XSB_CHK(dev_alloc(c, &c->coeff_nodal, (size_t)XSB_NSLOT * L.npn));
-  coeff_eval_kernel<<<nblk(nq), 256, 0, st>>>(L, c->mdl, c->lame, dT, c->coeff); KERNEL_OK();
-  q1_project_kernel<<<nblk(L.npn, 128), 128, 0, st>>>(L, dT, c->coeff, c->coeff_nodal); KERNEL_OK();
+  if (c->nodal_in) {   // coarse level of the monolithic -mg hierarchy: restricted nodal fields replace the model (femixedspace.c:2139-2215)
+    CUDA_OK(cudaMemcpyAsync(c->coeff_nodal, c->nodal_in, sizeof(double) * XSB_NSLOT * L.npn, cudaMemcpyDeviceToDevice, st));
+  } else {
+    coeff_eval_kernel<<<nblk(nq), 256, 0, st>>>(L, c->mdl, c->lame, dT, c->coeff); KERNEL_OK();
+    q1_project_kernel<<<nblk(L.npn, 128), 128, 0, st>>>(L, dT, c->coeff, c->coeff_nodal); KERNEL_OK();
+  }
   q1_interp_kernel<<<nblk(nq), 256, 0, st>>>(L, dT, c->coeff_nodal, c->coeff); KERNEL_OK();
   // operator-free mode (-xsb_matrix_free full): A and A00 are never stored (128^3: nnz(A) = 1.13e10 > 2^31 and 137 GB)
   { const std::string mfv = c->opt.str("xsb_matrix_free", "0"); c->no_A = (mfv == "full" || mfv == "2"); }

@@ -119,6 +119,7 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner)
   if (inner) *inner = 0;
   if (c->so.pc_type == 1) return vec_pmult(c, L.n, c->idiagA, r, z);
   if (c->so.pc_type == 0) return vec_copy(c, L.n, r, z);
+  if (c->so.pc_type == 3) return mmg_apply(c, r, z);
   // PCApply_FieldSplit_Schur, PC_FIELDSPLIT_SCHUR_FACT_UPPER
   double *yp = z + L.nu;
   if (c->so.p_pc == 0) XSB_CHK(ilu_apply(c, r + L.nu + c->own_p.off0, yp + c->own_p.off0)); else XSB_CHK(vec_pmult(c, L.np, c->mp_idiag, r + L.nu, yp));
@@ -140,9 +141,12 @@ static int read_solver_options(xsb_ctx c)
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_ksp_type %s not supported (gmres|fgmres)", ksp.c_str());
   const bool fs = o.flag("fs"), mg = o.flag("mg");
   if (fs && mg) return xsb_fail(c, XSB_ERR_SUP, "both -fs and -mg supplied");              // exSaddle.c:205
-  if (mg) return xsb_fail(c, XSB_ERR_SUP, "-mg (monolithic PCMG) is outside this library's scope");
-  if (o.integer("nlevels", 1) > 1) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified without -mg"); // exSaddle.c:208
-  if (fs) {
+  if (o.integer("nlevels", 1) > 1 && fs) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified with -fs");      // exSaddle.c:207
+  if (o.integer("nlevels", 1) > 1 && !mg) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified without -mg"); // exSaddle.c:208
+  if (mg) {
+    s.pc_type = 3;   // monolithic PCMG on the saddle operator (xsb_mmg.cu)
+    if (o.flag("fs_coarse")) return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse (fieldsplit coarse solver) is not implemented");
+  } else if (fs) {
     s.pc_type = 2;
     if (o.str("saddle_fieldsplit_u_pc_type", "") != "mg" || o.str("saddle_fieldsplit_u_ksp_type", "") != "gcr" || o.str("saddle_fieldsplit_p_ksp_type", "") != "preonly")
       return xsb_fail(c, XSB_ERR_SUP, "-fs is supported with the abf.opts tree: fieldsplit_u gcr+mg, fieldsplit_p preonly");
@@ -203,6 +207,7 @@ int ksp_setup(xsb_ctx c)
   if (!c->red) { XSB_CHK(dev_alloc(c, &c->red, (size_t)592 * 8)); XSB_CHK(dev_alloc(c, &c->scal, 256)); CUDA_OK(cudaMallocHost(&c->red_h, sizeof(double) * 256)); }
   if (!c->w_t1) { XSB_CHK(dev_alloc(c, &c->w_t1, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->w_t2, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->xdev, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->bdev, (size_t)L.n)); }
   if (c->so.pc_type == 1) { XSB_CHK(dev_alloc(c, &c->idiagA, (size_t)L.n)); XSB_CHK(csr_diag_inv(c, c->A, c->idiagA)); }
+  if (c->so.pc_type == 3) XSB_CHK(mmg_setup(c));
   if (c->so.pc_type == 2) {
     if (c->so.matrix_free) XSB_CHK(mf_setup(c));
     XSB_CHK(mg_setup(c));

@@ -83,6 +83,18 @@ int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, 
   KERNEL_OK(); return 0;
 }
 
+// scalar (pressure-lattice) transfers of the monolithic -mg path: the same stencils with one dof per node
+int mg_restrict_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny, int cnz, const double *rf, double *bc)
+{
+  const int64_t nc = (int64_t)cnx * cny * cnz;
+  k_restrict<1><<<nblk(nc, 128), 128, 0, c->stream>>>(fnx, fny, fnz, 0, cnx, cny, 0, cnz, rf, bc); KERNEL_OK(); return 0;
+}
+int mg_prolong_add_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny, const double *xc, double *xf)
+{
+  const int64_t nf = (int64_t)fnx * fny * fnz;
+  k_prolong_add<1><<<nblk(nf), 256, 0, c->stream>>>(fnx, fny, 0, fnz, 0, cnx, cny, xc, xf); KERNEL_OK(); return 0;
+}
+
 // ------------------------------------------------------------------ K9: Galerkin coarse operator
 __global__ void k_box_len(BoxPattern p, int64_t *len)
 {

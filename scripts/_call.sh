@@ -1,1 +1,1 @@
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/c8_launches_of.csv python bench.py --path operator-free --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/c8_ncu_bench.log 2>&1; tail -c 300 gpurun_out/c8_ncu_bench.log; wc -l gpurun_out/c8_launches_of.csv
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/c9_pytest.log 2>&1; tail -40 gpurun_out/c9_pytest.log | cut -c 1-400

@@ -338,3 +338,47 @@ def test_operator_free_mode_matches_oracle_and_assembled_path(name, lame, opts, 
     F = o.F()
     assert np.linalg.norm(F - o.mult(x)) <= 1.6e-8 * np.linalg.norm(F)
     g.close(); ga.close()
+
+
+# ------------------------------------------------------------------ monolithic -mg path
+@pytest.mark.parametrize("name", ["exSaddle3d_mg_1", "exSaddle2d_mg_1", "exSaddle2d_lame_mg_1", "exSaddle3d_lame_mg_1"])
+def test_golden_monolithic_mg_output_is_identical(kat, name):
+    """`-mg -nlevels L`: rediscretised levels, GMRES/Jacobi smoothers, LU coarse solve.  The program output (banner,
+    residual history as printed by -saddle_ksp_monitor_short, diagnostics) diffs clean against testref/*.ref."""
+    c, text, s, x = _run(kat, name)
+    ref = list(c["banner"]) + ["  Residual norms for saddle_ solve."] + \
+        ["%3d KSP Residual norm %s" % (i, t) for i, t in enumerate(c["residuals_text"])] + [l.rstrip() for l in c["diagnostics"]]
+    assert [l.rstrip() for l in text.rstrip("\n").split("\n")] == ref
+    assert s.iterations() == (len(c["residuals"]) - 1, 2)
+
+
+@pytest.mark.parametrize("opts,nsd,lame", [("-model 1 -mx 4 -my 8 -mz 4 -mg -nlevels 2", 3, False), ("-model 0 -mx 16 -mg -nlevels 4", 2, False),
+                                           ("-model 12 -mx 4 -mu1 10 -mg -nlevels 2", 3, True)])
+def test_monolithic_mg_matches_oracle(opts, nsd, lame):
+    from oracle.oracle_mg import MonolithicMG
+    full = opts + " -saddle_ksp_type fgmres -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi -saddle_mg_levels_ksp_max_it 10"
+    g = X.ExSaddle(full, nsd=nsd, lame=lame).assemble().ksp_setup()
+    M = MonolithicMG(full, nsd=nsd, lame=lame)   # configurations chosen to converge within one FGMRES cycle (<= 30 its, rtol 1e-5)
+    # one V-cycle on a random residual, then the whole solve
+    rng = np.random.default_rng(4)
+    r = rng.standard_normal(g.n)
+    zg, zo = g.pc_apply(r), M.pc_apply(r)
+    assert np.linalg.norm(zg - zo) <= 1e-9 * np.linalg.norm(zo)
+    x = g.solve(); xo, its, reason, ho = M.solve()
+    assert g.iterations() == (its, reason)
+    h = g.history()
+    assert np.max(np.abs(h - ho)) <= 1e-9 * ho[0]
+    big = ho >= 1e-3 * ho[0]
+    assert np.max(np.abs(h - ho)[big] / ho[big]) <= 1e-8
+    assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+    g.close()
+
+
+def test_monolithic_mg_option_errors_like_reference():
+    for opts, frag in (("-mx 6 -mg -nlevels 3", "incompatible with problem size"), ("-mx 8 -mg -nlevels 1", "-nlevels < 2 specified with -mg"),
+                       ("-mx 2 -mg -nlevels 3", "Too much refinement"), ("-mx 8 -fs -mg -nlevels 2", "both -fs and -mg")):
+        g = X.ExSaddle(opts + " -saddle_ksp_type fgmres -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi", nsd=3).assemble()
+        with pytest.raises(X.XsbError) as e:
+            g.ksp_setup()
+        assert frag in str(e.value)
+        g.close()
