@@ -335,7 +335,9 @@ def main():
                     "aij_matmult": {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)", "ms": aij_ms, "bytes": aij_bytes,
                                     "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak}}
         os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
-        try:
+        try:   # outer iteration count of the ONE-rank solve: what the CPU sample is scaled by (per-rank ILU changes it on slabs)
+            if world > 1:
+                raise RuntimeError("keep the one-rank count")
             d = json.load(open(ITERS_FILE)) if os.path.exists(ITERS_FILE) else {}
             d[config_key(a)] = {"outer_its": its, "inner_its_total": int(sum(inner)), "reason": reason}
             json.dump(d, open(ITERS_FILE, "w"), indent=1, sort_keys=True)
