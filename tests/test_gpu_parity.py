@@ -382,3 +382,31 @@ def test_monolithic_mg_option_errors_like_reference():
             g.ksp_setup()
         assert frag in str(e.value)
         g.close()
+
+
+# ------------------------------------------------------------------ BASELINE sizes against committed oracle fixtures
+@pytest.mark.parametrize("mx,levels", [(32, 5), (64, 6)])
+def test_baseline_size_history_matches_oracle_fixture(mx, levels):
+    """bench.py's workloads (configs[1] 32^3, configs[2] 64^3): the GPU residual history against the CPU oracle's, generated
+    once by tests/golden/make_oracle_64cubed.py (the 64^3 oracle solve takes ~25 min on 8 cores, so it is a fixture).
+    Bars (north_star): iteration count +-1, residual history within 1e-8 relative (KSP-relative)."""
+    import json, os
+    path = os.path.join(os.path.dirname(__file__), "golden", "oracle_%dcubed_history.json" % mx)
+    if not os.path.exists(path):
+        pytest.skip("fixture %s not generated" % path)
+    fx = json.load(open(path))
+    for extra in ("", " -xsb_matrix_free full"):
+        g = X.ExSaddle(fx["options"] + extra, nsd=3).assemble().ksp_setup()
+        x = g.solve()
+        its, reason = g.iterations()
+        h = g.history(); ho = np.array(fx["hist"])
+        assert reason == fx["reason"] and abs(its - fx["its"]) <= 1
+        n = min(len(h), len(ho))
+        assert np.max(np.abs(h[:n] - ho[:n])) <= 1e-8 * ho[0]
+        inner, inner_o = g.inner_iterations(), fx["inner_its"]
+        m = min(len(inner), len(inner_o))
+        assert sum(abs(a - b) for a, b in zip(inner[:m], inner_o[:m])) <= 2      # GCR counts of every outer iteration
+        for l in range(1, levels):
+            assert abs(g.chebyshev(l)[1] - fx["cheb_emax_est"][l]) <= 1e-8 * fx["cheb_emax_est"][l]
+        assert abs(np.linalg.norm(x) - fx["x_norm2"]) <= 1e-6 * fx["x_norm2"]
+        g.close()
