@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128, 2) mf_a00_kernel_v2(Lattice L, int colour
 #pragma unroll
   for (int b = 0; b < 3; ++b)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) fac[3 * b + q] = __ldg(eta + e * 27 + a + 3 * b + 9 * q);
+    for (int q = 0; q < 3; ++q) fac[3 * b + q] = __ldcs(eta + e * 27 + a + 3 * b + 9 * q);   // read once per product: evict-first, keep x / y in L2
   unsigned bcmask = 0;   // bit (9c + 3k + j): dof constrained (or lane idle)
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -291,11 +291,15 @@ __device__ __forceinline__ double mf_epi(const Epilogue &ep, int64_t i, double a
   }
 }
 // out = epilogue( isbc ? x : (K x) ): identity rows of the constrained dofs + the fused smoother update
-__global__ void mf_epilogue_kernel(int64_t n, const unsigned char *__restrict__ isbc, const double *__restrict__ x, const double *__restrict__ kx,
+// The accumulator kx is zeroed as it is read, so the next product needs no memset pass (it starts zero: dev_alloc).
+__global__ void mf_epilogue_kernel(int64_t n, const unsigned char *__restrict__ isbc, const double *__restrict__ x, double *kx,
                                    double *__restrict__ out, Epilogue ep)
 {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = mf_epi(ep, i, (isbc && isbc[i]) ? x[i] : kx[i]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = kx[i]; kx[i] = 0.0;
+    if (isbc && isbc[i]) v = x[i];
+    out[i] = mf_epi(ep, i, v);
+  }
 }
 
 int mf_setup(xsb_ctx c)
@@ -337,7 +341,6 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
   const double *eta = c->coeff;   // slot C_ETA (eta, or mu for LAME)
   MfTabS TS; { MfTab T0; host_mf_tab(T0);
     for (int q = 0; q < 3; ++q) { TS.w[q] = T0.w[q]; for (int n = 0; n < 3; ++n) { TS.N[q][n] = T0.N[q][n]; TS.Dx[q][n] = T0.D[q][n] / L.hu[0]; TS.Dy[q][n] = T0.D[q][n] / L.hu[1]; TS.Dz[q][n] = T0.D[q][n] / L.hu[2]; } } }
-  CUDA_OK(cudaMemsetAsync(c->mf_tmp, 0, sizeof(double) * L.nu, st));
   if (c->so.mf_kernel == 1) {
     for (int col = 0; col < 8; ++col) {
       const int ci = col & 1, cj = (col >> 1) & 1, ck = (col >> 2) & 1;
