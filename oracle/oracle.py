@@ -44,7 +44,7 @@ class Solver(C.Structure):
                 ("mg_levels", C.c_int), ("cheb_its", C.c_int), ("esteig", C.c_double * 4),
                 ("esteig_steps", C.c_int), ("noise", C.c_int), ("n_cheb_fixed", C.c_int),
                 ("cheb_emin", C.c_double * XO_MAX_LEVELS), ("cheb_emax", C.c_double * XO_MAX_LEVELS),
-                ("p_pc", C.c_int), ("max_outer_sample", C.c_int)]
+                ("p_pc", C.c_int), ("max_outer_sample", C.c_int), ("p_blocks", C.c_int)]
 
 
 class Result(C.Structure):
@@ -226,6 +226,7 @@ def make_solver(o):
     s.n_cheb_fixed = n
     ppc = o.get("saddle_fieldsplit_p_pc_type", "bjacobi")
     s.p_pc = {"bjacobi": 0, "ilu": 0, "jacobi": 1}[ppc]
+    s.p_blocks = int(o.get("xo_p_blocks", 1))   # bjacobi blocks = ranks of the slab partition being mirrored
     return s
 
 

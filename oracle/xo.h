@@ -65,6 +65,7 @@ typedef struct {
   double cheb_emin[XO_MAX_LEVELS], cheb_emax[XO_MAX_LEVELS];
   int    p_pc;            /* XO_PPC_ILU0 (bjacobi/ilu) or XO_PPC_JACOBI */
   int    max_outer_sample; /* >0: stop after this many outer its (CPU-baseline sample) */
+  int    p_blocks;         /* bjacobi blocks of the pressure PC: z-slabs of pressure planes like the product's N-rank slab partition (0/1 = one block) */
 } xo_solver;
 
 typedef struct {

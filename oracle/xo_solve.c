@@ -707,8 +707,27 @@ int xo_pc_setup(xo_problem *P, const xo_solver *s, xo_result *res)
       } else if (cheb_estimate(L, s)) return xo_fail(P, "Chebyshev eigenvalue estimate failed");
     }
     if (s->p_pc == XO_PPC_ILU0) {
+      const double *ma = P->ma; double *blk = NULL;
       P->mp_lu = (double *)malloc(sizeof(double) * P->mnnz);
-      if (xo_ilu0((int)P->np, P->mia, P->mja, P->ma, P->mp_lu)) return xo_fail(P, "ILU(0) of Mpscaled failed");
+      if (s->p_blocks > 1) {
+        /* PCBJACOBI with one block per rank (SURVEY 8e caveat 2): rank r owns the pressure planes of its element layers
+           [k0,k1) (mz/N each, remainder to the low ranks; the last rank also owns the top plane), i.e. the product's slab
+           rule.  ILU(0) of the block-diagonal part = ILU(0) of Mp with the cross-block entries set to zero (no update can
+           reach them: every l_ik u_kj with (i,j) across blocks has one cross-block factor). */
+        const int mz = P->PZ - 1, nb = s->p_blocks, q = mz / nb, rr = mz % nb; const int64_t pn = (int64_t)P->PX * P->PY;
+        int64_t i; int k;
+        if (P->prm.nsd != 3 || mz < nb) return xo_fail(P, "p_blocks needs a 3-D mesh with at least one element layer per block");
+        blk = (double *)malloc(sizeof(double) * P->mnnz);
+        #define XO_BLOCK_OF(plane) ((plane) >= mz ? nb - 1 : ((plane) < rr * (q + 1) ? (plane) / (q + 1) : rr + ((plane) - rr * (q + 1)) / q))
+        for (i = 0; i < P->np; ++i) {
+          const int bi = XO_BLOCK_OF((int)(i / pn));
+          for (k = P->mia[i]; k < P->mia[i + 1]; ++k) blk[k] = XO_BLOCK_OF((int)(P->mja[k] / pn)) == bi ? P->ma[k] : 0.0;
+        }
+        #undef XO_BLOCK_OF
+        ma = blk;
+      }
+      if (xo_ilu0((int)P->np, P->mia, P->mja, ma, P->mp_lu)) { free(blk); return xo_fail(P, "ILU(0) of Mpscaled failed"); }
+      free(blk);
     } else {
       xo_csr M; M.n = (int)P->np; M.m = M.n; M.ia = P->mia; M.ja = P->mja; M.a = P->ma; M.nnz = P->mnnz;
       P->mp_idiag = jacobi_idiag(&M);

@@ -26,3 +26,17 @@ def test_slab_solve_matches_single_gpu(n):
            "--master-port", str(29540 + n), os.path.join(ROOT, "scripts", "slab_check.py"), "8"]
     r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "SLAB_CHECK PASS" in r.stdout, r.stdout[-4000:]
+    # bjacobi/ILU(0) on the pressure block is per rank, so its iteration counts depend on the rank count: compare them
+    # with the oracle run on the same block structure (SURVEY 8e caveat 2)
+    import json
+    from oracle import oracle as O
+    res = json.load(open(os.path.join(ROOT, "gpurun_out", "slab_check_%d.json" % n)))["abf_bjacobi_ilu"]
+    its_o, inner_o = _oracle_bjacobi(O, n)
+    assert res["its"][0] == its_o and res["inner"] == inner_o[:len(res["inner"])]
+
+
+def _oracle_bjacobi(O, nblocks, mx=8):
+    abf = " ".join(l for l in O.ABF_OPTS.split("\n") if l.strip())
+    p = O.Problem(abf + " -saddle_fieldsplit_p_pc_type bjacobi -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8 -xo_p_blocks %d" % (mx, nblocks), nsd=3)
+    x, r = p.solve()
+    return r.its, [int(v) for v in r.inner_its[:r.n_inner]]

@@ -3,10 +3,14 @@
 tests/golden/testref_kat.json holds the numbers extracted from /root/reference/testref/*.ref and the
 option strings of /root/reference/Makefile:254-513 (tests/golden/make_golden.py).  No GPU needed.
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _sig(x, ref_text):
@@ -288,3 +292,34 @@ def test_monolithic_mg_option_errors():
         MonolithicMG("-mx 6 -mg -nlevels 3 -saddle_ksp_type fgmres -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi", nsd=3)   # 6 % 4 != 0 (exSaddle.c:220)
     with pytest.raises(ValueError):
         MonolithicMG("-mx 8 -mg -nlevels 1 -saddle_ksp_type fgmres -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi", nsd=3)   # exSaddle.c:209
+
+
+# ---- bjacobi blocks = ranks of the slab partition (SURVEY 8e caveat 2): the oracle predicts the multi-GPU iteration counts ----
+def test_bjacobi_block_oracle_matches_recorded_multi_gpu_runs():
+    """profiles/r01_slab_check_n{2,4}.json are the product's 2- and 4-GPU runs of the 8^3 ABF case with bjacobi/ILU(0) per rank
+    (scripts/slab_check.py on B200s).  The oracle with the same block structure gives the same outer and inner counts."""
+    import json
+    abf = " ".join(l for l in O.ABF_OPTS.split("\n") if l.strip())
+    base = abf + " -saddle_fieldsplit_p_pc_type bjacobi -model 6 -mx 8 -eta1 100 -saddle_ksp_rtol 1e-8"
+    x1, r1 = O.Problem(base, nsd=3).solve()
+    xb, rb = O.Problem(base + " -xo_p_blocks 1", nsd=3).solve()
+    assert r1.its == rb.its and np.allclose(r1.hist[:r1.nhist], rb.hist[:rb.nhist], rtol=1e-9, atol=0)   # one block = plain ILU(0) (OpenMP reductions: not bitwise)
+    for n in (2, 4):
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_slab_check_n%d.json" % n)))["abf_bjacobi_ilu"]
+        x, r = O.Problem(base + " -xo_p_blocks %d" % n, nsd=3).solve()
+        assert r.reason == 2 and r.its == rec["its"][0]
+        assert [int(v) for v in r.inner_its[:len(rec["inner"])]] == rec["inner"]
+        assert r.its != r1.its                                                              # the block structure matters
+
+
+def test_recorded_multi_gpu_iteration_counts_at_64cubed_match_block_oracle():
+    """BASELINE 64^3 workload on 2 and 8 B200s (profiles/r01_bench_64cubed_n2_v2.json, r01_bench_64cubed_n8.json) against the
+    oracle with 2 / 8 bjacobi blocks (tests/golden/oracle_64cubed_bjacobi_blocks.json, made by make_oracle_bjacobi_blocks.py):
+    45 and 51 outer iterations on both sides; one rank / one block: 42 (oracle_64cubed_history.json)."""
+    import json
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_64cubed_bjacobi_blocks.json")))
+    for n, prof in ((2, "r01_bench_64cubed_n2_v2.json"), (8, "r01_bench_64cubed_n8.json")):
+        rec = json.load(open(os.path.join(ROOT, "profiles", prof)))
+        assert rec["n_gpus"] == n and rec["solve"]["reason"] == 2 == fx[str(n)]["reason"]
+        assert rec["solve"]["outer_its"] == fx[str(n)]["its"]
+        assert abs(rec["solve"]["inner_gcr_its"] - sum(fx[str(n)]["inner"])) <= 1
