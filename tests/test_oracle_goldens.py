@@ -303,7 +303,8 @@ def test_bjacobi_block_oracle_matches_recorded_multi_gpu_runs():
     base = abf + " -saddle_fieldsplit_p_pc_type bjacobi -model 6 -mx 8 -eta1 100 -saddle_ksp_rtol 1e-8"
     x1, r1 = O.Problem(base, nsd=3).solve()
     xb, rb = O.Problem(base + " -xo_p_blocks 1", nsd=3).solve()
-    assert r1.its == rb.its and np.allclose(r1.hist[:r1.nhist], rb.hist[:rb.nhist], rtol=1e-9, atol=0)   # one block = plain ILU(0) (OpenMP reductions: not bitwise)
+    h1, hb = np.array(r1.hist[:r1.nhist]), np.array(rb.hist[:rb.nhist])
+    assert r1.its == rb.its and np.max(np.abs(h1 - hb)) <= 1e-10 * h1[0]   # one block = plain ILU(0) (OpenMP reductions: not bitwise)
     for n in (2, 4):
         rec = json.load(open(os.path.join(ROOT, "profiles", "r01_slab_check_n%d.json" % n)))["abf_bjacobi_ilu"]
         x, r = O.Problem(base + " -xo_p_blocks %d" % n, nsd=3).solve()
