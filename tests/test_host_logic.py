@@ -120,3 +120,35 @@ def test_product_never_imports_the_oracle():
                     txt = open(os.path.join(root, f)).read()
                     assert "oracle" not in txt.lower().replace("no oracle", ""), os.path.join(root, f)
                     assert "libxo" not in txt and "xo_" not in txt, os.path.join(root, f)
+
+
+# ------------------------------------------------------------------ bench.py host logic (no GPU)
+def test_bench_reference_arm_line_shape():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): one JSON line with the contract's keys, on a tiny mesh."""
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--mx", "8", "--levels", "3", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "dtype", "config", "cpu_baseline", "e2e"):
+        assert k in d
+    assert d["impl"] == "reference" and d["higher_is_better"] is False and d["dtype"] == "f64" and d["unit"] == "s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "outer FGMRES" in d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_algorithmic_bytes_and_path_choice():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py")); b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    # SURVEY 8d: BAIJ(3) A00 at 64^3 = 10.372 GB for a plain product (x, y streams), CSR full A = 17.183 GB
+    nun = 129 ** 3
+    per_dir = sum(3 if (i % 2 or i in (0, 128)) else 5 for i in range(129))   # coupling width of node i along one direction (range_uu)
+    nblk = per_dir ** 3
+    bytes_plain = b.a00_bytes((3 * nun, 3 * nun, 9 * nblk, 3), [1, 0, 0, 0])
+    assert abs(bytes_plain - 10.372e9) < 0.01e9
+    assert b.a00_bytes((3 * nun, 3 * nun, 9 * nblk, 3), [0, 0, 0, 1]) > bytes_plain     # Chebyshev step streams 3 more vectors
+    # 32-bit PetscInt: the assembled operator needs nnz(A) per rank < 2^31 (5420 nnz per element at large m)
+    assert 5420.0 * 64 ** 3 < 2.0e9 and 5420.0 * 128 ** 3 / 4 > 2.0e9 and 5420.0 * 128 ** 3 / 8 < 2.0e9
