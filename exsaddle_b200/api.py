@@ -41,6 +41,7 @@ def lib():
             "xsb_mat_get_info": [vp, C.c_int, i64p, i64p, i64p, C.POINTER(C.c_int)],
             "xsb_mat_get_csr": [vp, C.c_int, i32p, i32p, dp], "xsb_mat_mult": [vp, C.c_int, dp, dp],
             "xsb_mat_mult_dev": [vp, C.c_int, vp, vp], "xsb_mat_get_diagonal": [vp, C.c_int, dp],
+            "xsb_mat_mult_transpose": [vp, C.c_int, dp, dp], "xsb_ksp_view": [vp, C.c_char_p, C.c_int],
             "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
             "xsb_ksp_setup": [vp], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
             "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
@@ -290,6 +291,15 @@ class ExSaddle:
         v = [C.c_double() for _ in range(4)]
         self._chk(self.L.xsb_ksp_get_chebyshev(self.h, level, *[C.byref(t) for t in v]))
         return tuple(t.value for t in v)
+
+    def view(self):
+        buf = C.create_string_buffer(16384)
+        self._chk(self.L.xsb_ksp_view(self.h, buf, len(buf))); return buf.value.decode()
+
+    def mat_mult_transpose(self, which, x):
+        rows, cols, _, _ = self.mat_info(which)
+        x = np.ascontiguousarray(x, dtype=np.float64); y = np.empty(cols)
+        self._chk(self.L.xsb_mat_mult_transpose(self.h, which, _dp(x), _dp(y))); return y
 
     def timing(self):
         a, b = C.c_double(), C.c_double()

@@ -248,6 +248,15 @@ int xsb_mat_mult(xsb_ctx c, int which, const double *x, double *y)
   return rc;
 }
 
+int xsb_mat_mult_transpose(xsb_ctx c, int which, const double *x, double *y)
+{
+  NEED_DEVICE(c);
+  // the saddle operator and its diagonal blocks are symmetric (MatZeroRowsColumns keeps the symmetry); the gradient and
+  // divergence blocks are each other's transposes by construction (the same g[d] goes to both, femixedspace.c:2584-2590)
+  if (which == XSB_MAT_A01) which = XSB_MAT_A10; else if (which == XSB_MAT_A10) which = XSB_MAT_A01;
+  return xsb_mat_mult(c, which, x, y);
+}
+
 int xsb_mat_get_diagonal(xsb_ctx c, int which, double *d)
 {
   NEED_DEVICE(c);
@@ -392,6 +401,39 @@ int xsb_ksp_get_chebyshev(xsb_ctx c, int level, double *emin_est, double *emax_e
   return XSB_OK;
 }
 int xsb_ksp_get_timing(xsb_ctx c, double *setup_ms, double *solve_ms) { if (!c) return XSB_ERR_ARG; if (setup_ms) *setup_ms = c->setup_ms; if (solve_ms) *solve_ms = c->solve_ms; return XSB_OK; }
+int xsb_ksp_view(xsb_ctx c, char *buf, int buflen)
+{
+  if (!c || !buf || buflen < 1) return XSB_ERR_ARG;
+  if (!c->ksp_ready) return xsb_fail(c, XSB_ERR_ORDER, "xsb_ksp_view before xsb_ksp_setup");
+  const SolverOpts &s = c->so; std::string o; char t[512];
+  auto add = [&](const char *fmt, auto... a) { snprintf(t, sizeof(t), fmt, a...); o += t; };
+  add("KSP Object: (saddle_) %d GPU(s)\n  type: %s\n    restart=%d, using Classical (unmodified) Gram-Schmidt Orthogonalization with no iterative refinement\n",
+      c->slab.nranks, s.ksp_type == 1 ? "fgmres" : "gmres", s.restart);
+  add("  maximum iterations=%d, initial guess is zero\n  tolerances:  relative=%g, absolute=%g, divergence=%g.\n", s.max_it, s.rtol, s.atol, s.dtol);
+  add("  %s preconditioning\n  using %s norm type for convergence test\n", s.right ? "right" : "left", s.right ? "UNPRECONDITIONED" : "PRECONDITIONED");
+  add("PC Object: (saddle_)\n");
+  if (s.pc_type == 0) add("  type: none\n");
+  else if (s.pc_type == 1) add("  type: jacobi\n");
+  else if (s.pc_type == 3) add("  type: mg\n    type is MULTIPLICATIVE, levels=%d cycles=v\n      Not using Galerkin computed coarse grid matrices\n    smoothers: gmres + jacobi, exactly %d iterations; coarse: dense LU (pivoted inverse on the device)\n",
+                               c->opt.integer("nlevels", 1), c->opt.integer("saddle_mg_levels_ksp_max_it", 2));
+  else {
+    add("  type: fieldsplit\n    FieldSplit with Schur preconditioner, factorization UPPER\n    Preconditioner for the Schur complement formed from user provided matrix\n");
+    add("    KSP solver for A00 block: (saddle_fieldsplit_u_) gcr, restart=%d, relative=%g; PC mg, MULTIPLICATIVE, levels=%d cycles=v, Galerkin coarse operators\n", s.u_restart, s.u_rtol, c->nlev);
+    add("      fine-level products: %s\n", c->no_A ? "operator-free (sum-factorised Q2 element kernel; A and A00 not stored)" : s.matrix_free ? "matrix-free element kernel (A00 also assembled)" : "assembled BAIJ");
+    for (int l = 0; l < c->nlev; ++l) {
+      const Level &L = c->lev[l]; const long long rows = (long long)L.A.nb * L.A.bs, nz = (long long)L.A.nblk * L.A.bs * L.A.bs;
+      if (l == 0) add("      level 0 (coarse): preonly + lu (dense inverse), rows=%lld, total: nonzeros=%lld, bs=%d\n", rows, nz, L.A.bs);
+      else add("      level %d: chebyshev + jacobi, maximum iterations=%d, eigenvalue estimates used:  min = %g, max = %g%s, rows=%lld, total: nonzeros=%lld, bs=%d%s\n",
+               l, s.cheb_its, L.emin, L.emax, s.n_cheb_fixed ? " (set explicitly)" : "", rows, nz, L.A.bs, L.dist ? ", z-slab distributed" : L.rowpart ? ", replicated, products row-partitioned" : "");
+    }
+    add("    KSP solver for S = A11 - A10 inv(A00) A01: (saddle_fieldsplit_p_) preonly; PC %s on Mpscaled (rows=%d, nonzeros=%lld)\n",
+        s.p_pc == 0 ? "bjacobi, one block per GPU, ilu(0) in natural ordering" : "jacobi", c->Mp.n, (long long)c->Mp.nnz);
+  }
+  add("  linear system matrix: rows=%lld, cols=%lld, total: nonzeros=%lld%s\n", (long long)c->lat.n, (long long)c->lat.n, (long long)c->A.nnz, c->no_A ? " (not stored)" : ", type aij");
+  snprintf(buf, buflen, "%s", o.c_str());
+  return XSB_OK;
+}
+
 int xsb_ksp_get_counters(xsb_ctx c, int64_t out[8])
 {
   if (!c || !out) return XSB_ERR_ARG;

@@ -81,6 +81,8 @@ int xsb_mat_get_info(xsb_ctx ctx, int which, int64_t *rows, int64_t *cols, int64
 int xsb_mat_get_csr(xsb_ctx ctx, int which, int32_t *ia, int32_t *ja, double *a); /* host out; NULL to skip */
 int xsb_mat_mult(xsb_ctx ctx, int which, const double *x, double *y);            /* host pointers */
 int xsb_mat_mult_dev(xsb_ctx ctx, int which, const double *x, double *y);        /* device pointers */
+int xsb_mat_mult_transpose(xsb_ctx ctx, int which, const double *x, double *y);  /* MatMultTranspose, host pointers: A, A00, A11, Mp are
+                                                                                    symmetric; A01^T = A10 (femixedspace.c:2584-2590) */
 int xsb_mat_get_diagonal(xsb_ctx ctx, int which, double *d);
 int xsb_vec_get_rhs(xsb_ctx ctx, double *F);                                      /* F of exSaddle.c:263-281 */
 int xsb_get_bc(xsb_ctx ctx, int32_t *idx, double *val);                           /* u_is_global / u_bc_global */
@@ -105,6 +107,9 @@ int xsb_ksp_get_history(xsb_ctx ctx, double *hist, int cap, int *n);
 int xsb_ksp_get_inner_iterations(xsb_ctx ctx, int *its, int cap, int *n);     /* fieldsplit_u GCR counts */
 int xsb_ksp_get_chebyshev(xsb_ctx ctx, int level, double *emin_est, double *emax_est, double *emin, double *emax);
 int xsb_ksp_get_timing(xsb_ctx ctx, double *setup_ms, double *solve_ms);      /* CUDA-event times */
+/* KSPView / PCView (pc->ops->view, pcildl.c:429-456; -saddle_ksp_view): the solver tree in use, level sizes, nonzeros and
+   Chebyshev bounds, as text (PETSc-like layout, not byte-identical to PETSc's viewer) */
+int xsb_ksp_view(xsb_ctx ctx, char *buf, int buflen);
 /* counters of the last solve: [0] fine-level A00 block SpMV launches [1] full-A SpMV launches [2] all kernel
    launches [3] average fine-level A00 SpMV device time in ns (CUDA-event pairs on the launching stream around
    every such launch when -xsb_time_kernels is set; read back after the solve, no extra synchronisation)

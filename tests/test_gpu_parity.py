@@ -415,3 +415,24 @@ def test_baseline_size_history_matches_oracle_fixture(mx, levels):
             assert abs(g.chebyshev(l)[1] - fx["cheb_emax_est"][l]) <= 1e-12 * fx["cheb_emax_est"][l]
         assert abs(np.linalg.norm(x) - fx["x_norm2"]) <= 1e-7 * fx["x_norm2"]
         g.close()
+
+
+# ------------------------------------------------------------------ MatMultTranspose / KSPView entry points
+def test_mult_transpose_and_view():
+    opts = ABF + " -model 6 -mx 4 -eta1 100 -saddle_fieldsplit_u_pc_mg_levels 2"
+    g = X.ExSaddle(opts, nsd=3).assemble().ksp_setup()
+    o = O.Problem(opts, nsd=3)
+    rng = np.random.default_rng(9)
+    for which, rb, cb in ((X.MAT_A01, 0, 1), (X.MAT_A10, 1, 0), (X.MAT_A11, 1, 1), (X.MAT_A00, 0, 0)):
+        M = o.submatrix(rb, cb).scipy()
+        x = rng.standard_normal(M.shape[0])
+        yo = M.T @ x
+        y = g.mat_mult_transpose(which, x)
+        assert y.shape == yo.shape and np.linalg.norm(y - yo) <= 1e-12 * max(np.linalg.norm(yo), 1e-300)
+    x = rng.standard_normal(o.n)
+    yo = o.A().scipy().T @ x
+    assert np.linalg.norm(g.mat_mult_transpose(X.MAT_A, x) - yo) <= 1e-12 * np.linalg.norm(yo)
+    text = g.view()
+    for frag in ("type: fgmres", "FieldSplit with Schur preconditioner, factorization UPPER", "level 1: chebyshev + jacobi", "ilu(0)", "type aij"):
+        assert frag in text, text
+    g.close()
