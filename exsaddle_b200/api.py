@@ -42,6 +42,8 @@ def lib():
             "xsb_mat_get_csr": [vp, C.c_int, i32p, i32p, dp], "xsb_mat_mult": [vp, C.c_int, dp, dp],
             "xsb_mat_mult_dev": [vp, C.c_int, vp, vp], "xsb_mat_get_diagonal": [vp, C.c_int, dp],
             "xsb_mat_mult_transpose": [vp, C.c_int, dp, dp], "xsb_ksp_view": [vp, C.c_char_p, C.c_int],
+            "xsb_dump_operator": [vp, C.c_int, C.c_char_p], "xsb_dump_vector": [vp, dp, C.c_int64, C.c_char_p],
+            "xsb_write_petsc_mat": [C.c_char_p, C.c_int64, C.c_int64, i32p, i32p, dp], "xsb_write_petsc_vec": [C.c_char_p, C.c_int64, dp],
             "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
             "xsb_ksp_setup": [vp], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
             "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
@@ -301,6 +303,13 @@ class ExSaddle:
         x = np.ascontiguousarray(x, dtype=np.float64); y = np.empty(cols)
         self._chk(self.L.xsb_mat_mult_transpose(self.h, which, _dp(x), _dp(y))); return y
 
+    def dump_operator(self, which, path):
+        self._chk(self.L.xsb_dump_operator(self.h, which, path.encode()))
+
+    def dump_vector(self, x, path):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self._chk(self.L.xsb_dump_vector(self.h, _dp(x), len(x), path.encode()))
+
     def timing(self):
         a, b = C.c_double(), C.c_double()
         self._chk(self.L.xsb_ksp_get_timing(self.h, C.byref(a), C.byref(b))); return a.value, b.value
@@ -319,3 +328,37 @@ class ExSaddle:
     def diagnostics(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64); out = np.empty(5 * self.nsd + 5)
         self._chk(self.L.xsb_diagnostics(self.h, _dp(x), _dp(out))); return out
+
+
+def write_petsc_mat(path, ia, ja, a, shape):
+    """PETSc binary Mat file from host CSR arrays (no GPU needed)."""
+    ia = np.ascontiguousarray(ia, np.int32); ja = np.ascontiguousarray(ja, np.int32); a = np.ascontiguousarray(a, np.float64)
+    rc = lib().xsb_write_petsc_mat(path.encode(), shape[0], shape[1], _ip(ia), _ip(ja), _dp(a))
+    if rc:
+        raise XsbError(rc, "cannot write %s" % path)
+
+
+def write_petsc_vec(path, x):
+    x = np.ascontiguousarray(x, np.float64)
+    rc = lib().xsb_write_petsc_vec(path.encode(), len(x), _dp(x))
+    if rc:
+        raise XsbError(rc, "cannot write %s" % path)
+
+
+def read_petsc_binary(path):
+    """Reader for the files above (the layout PETSc's PetscBinaryIO.py / PetscBinaryRead.m read): returns
+    ("Mat", (ia, ja, a, shape)) or ("Vec", x)."""
+    raw = open(path, "rb").read()
+    cid = int(np.frombuffer(raw, ">i4", 1, 0)[0])
+    if cid == 1211214:
+        n = int(np.frombuffer(raw, ">i4", 1, 4)[0])
+        return "Vec", np.frombuffer(raw, ">f8", n, 8).astype(np.float64)
+    if cid == 1211216:
+        rows, cols, nnz = (int(v) for v in np.frombuffer(raw, ">i4", 3, 4))
+        lens = np.frombuffer(raw, ">i4", rows, 16).astype(np.int64)
+        ja = np.frombuffer(raw, ">i4", nnz, 16 + 4 * rows).astype(np.int32)
+        a = np.frombuffer(raw, ">f8", nnz, 16 + 4 * rows + 4 * nnz).astype(np.float64)
+        ia = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        assert len(raw) == 16 + 4 * rows + 12 * nnz
+        return "Mat", (ia, ja, a, (rows, cols))
+    raise ValueError("not a PETSc Mat/Vec binary file (class id %d)" % cid)

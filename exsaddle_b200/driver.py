@@ -26,8 +26,10 @@ def diagnostics_text(nsd, d):
     return lines
 
 
-def run_exsaddle(exe, options, options_file_dir=None):
-    """exe in {exSaddle2d, exSaddle3d, exSaddle2d_lame, exSaddle3d_lame}; returns (stdout_text, ExSaddle, x)."""
+def run_exsaddle(exe, options, options_file_dir=None, outdir="."):
+    """exe in {exSaddle2d, exSaddle3d, exSaddle2d_lame, exSaddle3d_lame}; returns (stdout_text, ExSaddle, x).
+    -dump_solution / -dump_operator / -dump_scaled_mass_matrix write PETSc binary files into `outdir` under the
+    reference's file names (exSaddle.c:488-501, 535-537)."""
     import os
     nsd = 2 if "2d" in exe else 3
     lame = "lame" in exe
@@ -62,4 +64,23 @@ def run_exsaddle(exe, options, options_file_dir=None):
             out.append("Linear saddle_ solve did not converge due to %s iterations %d" % (_REASON.get(reason, str(reason)), its))
     if "-diagnostics" in toks:
         out.extend(diagnostics_text(nsd, s.diagnostics(x)))
+    from .api import MAT_A, MAT_MP
+    if "-dump_solution" in toks:       # DumpSolution, exSaddle_io.c:76-88
+        out.append("Dumping solution vector to solution.petscbin.")
+        s.dump_vector(x, os.path.join(outdir, "solution.petscbin"))
+        out.append("Finished dumping vector to solution.petscbin.")
+    if "-dump_operator" in toks:       # DumpOperator, exSaddle_io.c:61-73 (finest level: operator_<nlevels-1>)
+        k = 0
+        if "-nlevels" in toks:
+            k = int(toks[toks.index("-nlevels") + 1]) - 1
+        name = "operator_%d.petscbin" % k
+        out.append("Dumping operator to %s. This could be very slow!" % name)
+        s.dump_operator(MAT_A, os.path.join(outdir, name))
+        out.append("Finished dumping operator to %s." % name)
+    if "-dump_scaled_mass_matrix" in toks:
+        if "-fs" not in toks:
+            raise ValueError("-dump_scaled_mass_matrix without -fs")   # exSaddle.c:213
+        out.append("Dumping operator to mpscaled.petscbin. This could be very slow!")
+        s.dump_operator(MAT_MP, os.path.join(outdir, "mpscaled.petscbin"))
+        out.append("Finished dumping operator to mpscaled.petscbin.")
     return "\n".join(out) + "\n", s, x

@@ -121,6 +121,16 @@ int xsb_get_stream(xsb_ctx ctx, void **stream);
 /* SaddleReportSolutionDiagnostics (exSaddle_io.c:7-58): out[5*nsd+5] = {1,2,inf,min,max} x comps, then p */
 int xsb_diagnostics(xsb_ctx ctx, const double *x /* host */, double *out);
 
+/* -------- PETSc binary dumps: DumpOperator / DumpSolution (exSaddle_io.c:61-88; -dump_operator -> operator_<k>.petscbin,
+   -dump_solution -> solution.petscbin, -dump_scaled_mass_matrix -> mpscaled.petscbin, exSaddle.c:488-501, 535-537).
+   The files are what PetscViewerBinaryOpen + MatView / VecView write (big-endian; Mat: 1211216, rows, cols, nnz, row
+   lengths, columns, values; Vec: 1211214, n, values) and load with PetscBinaryRead (octave_demo.m:10-12) / MatLoad. */
+int xsb_dump_operator(xsb_ctx ctx, int which, const char *path);
+int xsb_dump_vector(xsb_ctx ctx, const double *x /* host */, int64_t n, const char *path);
+/* the writers themselves: host arrays in, no GPU needed */
+int xsb_write_petsc_mat(const char *path, int64_t rows, int64_t cols, const int32_t *ia, const int32_t *ja, const double *a);
+int xsb_write_petsc_vec(const char *path, int64_t n, const double *x);
+
 /* -------- host-side index maps (no GPU needed; integer logic only) --------------------------------------- */
 /* columns of AIJ row `row` in ascending order (pattern of MatAssemble_Saddle_NULL, femixedspace.c:2306-2370) */
 int xsb_pattern_row(int nsd, int mx, int my, int mz, int64_t row, int32_t *cols, int cap);

@@ -436,3 +436,21 @@ def test_mult_transpose_and_view():
     for frag in ("type: fgmres", "FieldSplit with Schur preconditioner, factorization UPPER", "level 1: chebyshev + jacobi", "ilu(0)", "type aij"):
         assert frag in text, text
     g.close()
+
+
+def test_petsc_binary_dumps_of_operator_and_solution(tmp_path):
+    """-dump_operator / -dump_solution / -dump_scaled_mass_matrix (exSaddle.c:488-501, 535-537): the files hold exactly the
+    operator and solution the handle reports, in PETSc's binary layout, under the reference's file names."""
+    opts = ABF + " -model 6 -mx 4 -eta1 100 -saddle_fieldsplit_u_pc_mg_levels 2 -diagnostics -dump_solution -dump_operator -dump_scaled_mass_matrix"
+    text, s, x = X.run_exsaddle("exSaddle3d", opts, outdir=str(tmp_path))
+    assert "Dumping solution vector to solution.petscbin." in text and "Finished dumping operator to operator_0.petscbin." in text
+    kind, xs = X.read_petsc_binary(str(tmp_path / "solution.petscbin"))
+    assert kind == "Vec" and np.array_equal(xs, x)
+    ia, ja, a, shape = s.mat_csr(X.MAT_A)
+    kind, (ia2, ja2, a2, shape2) = X.read_petsc_binary(str(tmp_path / "operator_0.petscbin"))
+    assert kind == "Mat" and tuple(shape2) == tuple(shape) and np.array_equal(ia2, ia) and np.array_equal(ja2, ja) and np.array_equal(a2, a)
+    o = O.Problem(opts, nsd=3)
+    kind, (mia, mja, ma, mshape) = X.read_petsc_binary(str(tmp_path / "mpscaled.petscbin"))
+    M = o.Mp()
+    assert np.array_equal(mia, M.ia) and np.array_equal(mja, M.ja) and _relerr(ma, M.a) <= 1e-13
+    s.close()

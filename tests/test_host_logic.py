@@ -152,3 +152,32 @@ def test_bench_algorithmic_bytes_and_path_choice():
     assert b.a00_bytes((3 * nun, 3 * nun, 9 * nblk, 3), [0, 0, 0, 1]) > bytes_plain     # Chebyshev step streams 3 more vectors
     # 32-bit PetscInt: the assembled operator needs nnz(A) per rank < 2^31 (5420 nnz per element at large m)
     assert 5420.0 * 64 ** 3 < 2.0e9 and 5420.0 * 128 ** 3 / 4 > 2.0e9 and 5420.0 * 128 ** 3 / 8 < 2.0e9
+
+
+# ------------------------------------------------------------------ PETSc binary writers (no GPU)
+def test_petsc_binary_writers_byte_layout(tmp_path):
+    """The format PetscViewerBinaryOpen + MatView / VecView write (exSaddle_io.c:61-88): big-endian, class id first."""
+    import struct
+    ia = np.array([0, 2, 3, 5], np.int32); ja = np.array([0, 2, 1, 0, 2], np.int32); a = np.array([1.5, -2.0, 3.25, 4.0, 1e-300])
+    pm, pv = str(tmp_path / "operator_0.petscbin"), str(tmp_path / "solution.petscbin")
+    X.write_petsc_mat(pm, ia, ja, a, (3, 3))
+    want = struct.pack(">4i", 1211216, 3, 3, 5) + struct.pack(">3i", 2, 1, 2) + struct.pack(">5i", *ja) + struct.pack(">5d", *a)
+    assert open(pm, "rb").read() == want
+    x = np.array([0.0, -1.0, 2.5e10, np.pi])
+    X.write_petsc_vec(pv, x)
+    assert open(pv, "rb").read() == struct.pack(">2i", 1211214, 4) + struct.pack(">4d", *x)
+    kind, (ia2, ja2, a2, shape) = X.read_petsc_binary(pm)
+    assert kind == "Mat" and shape == (3, 3) and np.array_equal(ia2, ia) and np.array_equal(ja2, ja) and np.array_equal(a2, a)
+    kind, x2 = X.read_petsc_binary(pv)
+    assert kind == "Vec" and np.array_equal(x2, x)
+
+
+def test_petsc_binary_round_trip_of_the_oracle_operator(tmp_path):
+    from oracle import oracle as O
+    o = O.Problem("-model 6 -mx 3 -my 2 -mz 2 -eta1 10", nsd=3)
+    A = o.A()
+    path = str(tmp_path / "operator_0.petscbin")
+    X.write_petsc_mat(path, A.ia, A.ja, A.a, A.shape)
+    kind, (ia, ja, a, shape) = X.read_petsc_binary(path)
+    assert kind == "Mat" and shape == A.shape and np.array_equal(ia, A.ia) and np.array_equal(ja, A.ja) and np.array_equal(a, A.a)
+    assert os.path.getsize(path) == 16 + 4 * o.n + 12 * o.nnz
