@@ -25,6 +25,7 @@ template int dev_alloc<double>(xsb_ctx, double **, size_t);
 template int dev_alloc<int>(xsb_ctx, int **, size_t);
 template int dev_alloc<char>(xsb_ctx, char **, size_t);
 template int dev_alloc<unsigned char>(xsb_ctx, unsigned char **, size_t);
+template int dev_alloc<unsigned short>(xsb_ctx, unsigned short **, size_t);
 
 int dev_free_all(xsb_ctx c)
 {

@@ -454,3 +454,25 @@ def test_petsc_binary_dumps_of_operator_and_solution(tmp_path):
     M = o.Mp()
     assert np.array_equal(mia, M.ia) and np.array_equal(mja, M.ja) and _relerr(ma, M.a) <= 1e-13
     s.close()
+
+
+# ------------------------------------------------------------------ experimental kernels (opt-in options, off by default)
+@pytest.mark.skipif(__import__("os").environ.get("XSB_EXPERIMENTAL") != "1", reason="experimental variants: set XSB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("opts", ["-model 6 -mx 8 -eta1 1e4", "-model 1 -mx 4 -my 6 -mz 2", "-model 6 -mx 16 -eta1 100"])
+def test_experimental_windowed_ilu_matches_oracle(opts):
+    """-xsb_ilu_kernel 2 (single-CTA solve with an 8-wavefront ring of x in shared memory) against the oracle's sequential
+    forward / backward substitution, and against the default cluster kernel."""
+    full = "%s %s -saddle_fieldsplit_u_pc_mg_levels 2" % (ABF, opts)
+    g2 = X.ExSaddle(full + " -xsb_ilu_kernel 2", nsd=3).assemble().ksp_setup()
+    g1 = X.ExSaddle(full, nsd=3).assemble().ksp_setup()
+    o = O.Problem(full, nsd=3)
+    M = o.Mp(); lu = np.empty_like(M.a)
+    assert O.lib().xo_ilu0(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
+    rng = np.random.default_rng(13)
+    for _ in range(2):
+        bp = rng.standard_normal(o.np_)
+        xp = np.empty(o.np_); O.lib().xo_ilu0_solve(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(bp), O._dp(xp))
+        x2, x1 = g2.pc_schur_apply(bp), g1.pc_schur_apply(bp)
+        assert np.linalg.norm(x2 - xp) <= 1e-12 * np.linalg.norm(xp)
+        assert np.array_equal(x2, x1)      # same operations per row in the same order
+    g1.close(); g2.close()
