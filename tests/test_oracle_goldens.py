@@ -334,3 +334,47 @@ def test_reference_itself_moves_by_one_iteration_between_rank_counts(kat):
     assert a["options"] == b["options"] and (a["iterations"], b["iterations"]) == (145, 146)
     da, db = _nums(a["diagnostics"]), _nums(b["diagnostics"])
     assert np.allclose(da, db, rtol=1e-3, atol=1e-7) and not np.array_equal(da, db)
+
+
+def test_wavefront_window_of_the_pressure_ilu_sweeps():
+    """Claim behind the product's ILU(0) kernels (xsb_ilu.cu): on the 27-point pressure lattice row (i,j,k) only depends on rows of
+    the 7 previous wavefronts w = i + 2j + 4k, so (a) rows of one wavefront are independent and (b) an 8-slot ring of x suffices.
+    Emulated here on the oracle's factors: wavefront-ordered sweeps through an 8-slot ring reproduce the sequential solve exactly."""
+    o = O.Problem("-model 6 -mx 6 -my 5 -mz 4 -eta1 100", nsd=3)
+    M = o.Mp(); n = o.np_
+    lu = np.empty_like(M.a)
+    assert O.lib().xo_ilu0(n, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
+    px, py = 7, 6
+    node = np.arange(n); i, j, k = node % px, (node // px) % py, node // (px * py)
+    w = i + 2 * j + 4 * k
+    nw = int(w.max()) + 1
+    order = np.argsort(w, kind="stable"); off = np.concatenate([[0], np.cumsum(np.bincount(w, minlength=nw))])
+    pos = np.empty(n, int); pos[order] = np.arange(n) - off[w[order]]
+    maxw = int(np.max(np.diff(off)))
+    for r in range(n):      # dependency window
+        cols = M.ja[M.ia[r]:M.ia[r + 1]]
+        lower, upper = cols[cols < r], cols[cols > r]
+        assert np.all((w[r] - w[lower] >= 1) & (w[r] - w[lower] <= 7)) and np.all((w[upper] - w[r] >= 1) & (w[upper] - w[r] <= 7))
+    rng = np.random.default_rng(0); b = rng.standard_normal(n)
+    xs = np.empty(n); O.lib().xo_ilu0_solve(n, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(b), O._dp(xs))
+    ring = np.full(8 * maxw, np.nan); x = np.empty(n)
+    for lvl in range(nw):                                    # forward, unit lower
+        for r in order[off[lvl]:off[lvl + 1]]:
+            s = b[r]
+            for q in range(M.ia[r], M.ia[r + 1]):
+                c = M.ja[q]
+                if c < r:
+                    s -= lu[q] * ring[(w[c] & 7) * maxw + pos[c]]
+            ring[(lvl & 7) * maxw + pos[r]] = s; x[r] = s
+    for lvl in range(nw - 1, -1, -1):                        # backward, columns descending like MatSolve
+        for r in order[off[lvl]:off[lvl + 1]]:
+            s = x[r]; d = None
+            for q in range(M.ia[r + 1] - 1, M.ia[r] - 1, -1):
+                c = M.ja[q]
+                if c > r:
+                    s -= lu[q] * ring[(w[c] & 7) * maxw + pos[c]]
+                elif c == r:
+                    d = lu[q]
+            s = s * d                                        # the factor stores 1 / pivot (xo_ilu0)
+            ring[(lvl & 7) * maxw + pos[r]] = s; x[r] = s
+    assert not np.isnan(x).any() and np.linalg.norm(x - xs) <= 1e-13 * np.linalg.norm(xs)
