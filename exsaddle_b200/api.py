@@ -44,6 +44,8 @@ def lib():
             "xsb_mat_mult_transpose": [vp, C.c_int, dp, dp], "xsb_ksp_view": [vp, C.c_char_p, C.c_int],
             "xsb_dump_operator": [vp, C.c_int, C.c_char_p], "xsb_dump_vector": [vp, dp, C.c_int64, C.c_char_p],
             "xsb_write_petsc_mat": [C.c_char_p, C.c_int64, C.c_int64, i32p, i32p, dp], "xsb_write_petsc_vec": [C.c_char_p, C.c_int64, dp],
+            "xsb_view_fields": [vp, dp, C.c_char_p, C.c_char_p],
+            "xsb_write_vts": [C.c_char_p, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(C.c_char_p), dp, C.c_int64, C.c_int64],
             "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
             "xsb_ksp_setup": [vp], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
             "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
@@ -303,6 +305,10 @@ class ExSaddle:
         x = np.ascontiguousarray(x, dtype=np.float64); y = np.empty(cols)
         self._chk(self.L.xsb_mat_mult_transpose(self.h, which, _dp(x), _dp(y))); return y
 
+    def view_fields(self, x, outdir=".", tag=""):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self._chk(self.L.xsb_view_fields(self.h, _dp(x), outdir.encode(), tag.encode()))
+
     def dump_operator(self, which, path):
         self._chk(self.L.xsb_dump_operator(self.h, which, path.encode()))
 
@@ -362,3 +368,33 @@ def read_petsc_binary(path):
         assert len(raw) == 16 + 4 * rows + 12 * nnz
         return "Mat", (ia, ja, a, (rows, cols))
     raise ValueError("not a PETSc Mat/Vec binary file (class id %d)" % cid)
+
+
+def write_vts(path, dims, h, names, data, field_stride, node_stride):
+    """VTK XML StructuredGrid with raw appended data from a host array (no GPU needed); field f of node n = data[f*field_stride + n*node_stride]."""
+    data = np.ascontiguousarray(data, np.float64); hh = np.ascontiguousarray(h, np.float64)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    rc = lib().xsb_write_vts(path.encode(), dims[0], dims[1], dims[2], _dp(hh), len(names), arr, _dp(data), field_stride, node_stride)
+    if rc:
+        raise XsbError(rc, "cannot write %s" % path)
+
+
+def read_vts(path):
+    """Minimal reader of the files above: returns (dims, points[n,3], {name: values[n]})."""
+    import re
+    raw = open(path, "rb").read()
+    head, _, tail = raw.partition(b"<AppendedData encoding=\"raw\">\n_")
+    text = head.decode()
+    ext = [int(v) for v in re.search(r'WholeExtent="([^"]+)"', text).group(1).split()]
+    dims = (ext[1] + 1, ext[3] + 1, ext[5] + 1); n = dims[0] * dims[1] * dims[2]
+    out = {}; pts = None
+    for m in re.finditer(r'<DataArray type="Float64" Name="([^"]*)" NumberOfComponents="(\d)" format="appended" offset="(\d+)"', text):
+        name, nc, off = m.group(1), int(m.group(2)), int(m.group(3))
+        nbytes = int(np.frombuffer(tail, "<u8", 1, off)[0])
+        assert nbytes == 8 * nc * n
+        v = np.frombuffer(tail, "<f8", nc * n, off + 8).copy()
+        if name == "Position":
+            pts = v.reshape(n, 3)
+        else:
+            out[name] = v
+    return dims, pts, out

@@ -195,7 +195,7 @@ static int read_solver_options(xsb_ctx c)
   // monitor / view flags of the reference's command lines are accepted and handled by the caller
   o.has("saddle_ksp_monitor_short"); o.has("saddle_ksp_converged_reason"); o.has("saddle_ksp_view"); o.has("diagnostics");
   o.has("options_left"); o.has("saddle_fieldsplit_u_ksp_converged_reason"); o.has("twosolves");
-  o.has("dump_solution"); o.has("dump_operator"); o.has("dump_scaled_mass_matrix");   // written by the caller through xsb_dump_operator / xsb_dump_vector
+  o.has("dump_solution"); o.has("dump_operator"); o.has("dump_scaled_mass_matrix"); o.has("view_fields");   // written by the caller through xsb_dump_operator / xsb_dump_vector
   return 0;
 }
 

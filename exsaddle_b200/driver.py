@@ -65,6 +65,8 @@ def run_exsaddle(exe, options, options_file_dir=None, outdir="."):
     if "-diagnostics" in toks:
         out.extend(diagnostics_text(nsd, s.diagnostics(x)))
     from .api import MAT_A, MAT_MP
+    if "-view_fields" in toks:         # ViewFields(dm_saddle, X, ""), exSaddle.c:481-483
+        s.view_fields(x, outdir, "")
     if "-dump_solution" in toks:       # DumpSolution, exSaddle_io.c:76-88
         out.append("Dumping solution vector to solution.petscbin.")
         s.dump_vector(x, os.path.join(outdir, "solution.petscbin"))

@@ -131,6 +131,12 @@ int xsb_dump_vector(xsb_ctx ctx, const double *x /* host */, int64_t n, const ch
 int xsb_write_petsc_mat(const char *path, int64_t rows, int64_t cols, const int32_t *ia, const int32_t *ja, const double *a);
 int xsb_write_petsc_vec(const char *path, int64_t n, const double *x);
 
+/* ViewFields (exSaddle_io.c:128-177; -view_fields): <dir>/<tag>uv[w].vts (velocity components as scalar point fields on
+   the velocity lattice) and <dir>/<tag>p.vts, VTK XML StructuredGrid with raw appended data (loads in ParaView / VisIt). */
+int xsb_view_fields(xsb_ctx ctx, const double *x /* host */, const char *dir, const char *tag /* "" or "ref_" */);
+int xsb_write_vts(const char *path, int nx, int ny, int nz, const double h[3], int nfields, const char *const *names,
+                  const double *data, int64_t field_stride, int64_t node_stride);   /* the writer itself: host arrays, no GPU */
+
 /* -------- host-side index maps (no GPU needed; integer logic only) --------------------------------------- */
 /* columns of AIJ row `row` in ascending order (pattern of MatAssemble_Saddle_NULL, femixedspace.c:2306-2370) */
 int xsb_pattern_row(int nsd, int mx, int my, int mz, int64_t row, int32_t *cols, int cap);

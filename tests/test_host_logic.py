@@ -181,3 +181,22 @@ def test_petsc_binary_round_trip_of_the_oracle_operator(tmp_path):
     kind, (ia, ja, a, shape) = X.read_petsc_binary(path)
     assert kind == "Mat" and shape == A.shape and np.array_equal(ia, A.ia) and np.array_equal(ja, A.ja) and np.array_equal(a, A.a)
     assert os.path.getsize(path) == 16 + 4 * o.n + 12 * o.nnz
+
+
+def test_vts_writer_round_trip(tmp_path):
+    """ViewFields container (exSaddle_io.c:128-177): the interleaved velocity vector as scalar point fields u, v, w on the node
+    lattice with uniform coordinates; read back with an independent parser of the VTK XML appended-raw layout."""
+    nx, ny, nz, nsd = 5, 3, 4, 3
+    n = nx * ny * nz
+    xu = np.arange(nsd * n, dtype=np.float64) * 0.5 - 7.0        # node-major, component fastest (DMDA dof ordering)
+    path = str(tmp_path / "uvw.vts")
+    X.write_vts(path, (nx, ny, nz), (0.25, 0.5, 0.125), ["u", "v", "w"], xu, 1, nsd)
+    dims, pts, fields = X.read_vts(path)
+    assert dims == (nx, ny, nz) and sorted(fields) == ["u", "v", "w"]
+    for c, name in enumerate(("u", "v", "w")):
+        assert np.array_equal(fields[name], xu[c::nsd])
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    node = (i + nx * (j + ny * k)).ravel()
+    assert np.array_equal(pts[node], np.stack([0.25 * i.ravel(), 0.5 * j.ravel(), 0.125 * k.ravel()], axis=1))
+    head = open(path, "rb").read(400).decode(errors="replace")
+    assert 'type="StructuredGrid"' in head and 'byte_order="LittleEndian"' in head and 'WholeExtent="0 4 0 2 0 3"' in head
