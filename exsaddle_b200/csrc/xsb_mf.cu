@@ -372,8 +372,15 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
     if (chunk <= 0) chunk = L.mz;
     if (chunk >= L.mz) chunk = L.mz; else chunk &= ~1;   // even chunk starts keep the colour parity pattern regular
     int launch = 0;
-    for (int kz0 = 0; kz0 < L.mz; kz0 += chunk) {
-      const int kz1 = kz0 + chunk < L.mz ? kz0 + chunk : L.mz;
+    // Slabs: only the element layers that touch an owned node plane are needed, [k0-1, k1) of the local [k0-2, k1+1); the two
+    // extra ghost layers exist for the assembled Galerkin rows.  EXPERIMENTAL, opt-in (-xsb_mf_owned_layers): not yet run on >1 GPU.
+    int zlo = 0, zhi = L.mz;
+    if (c->slab.nranks > 1 && isbc && c->opt.flag("xsb_mf_owned_layers")) {
+      zlo = c->slab.k0 - c->slab.e0 - 1; if (zlo < 0) zlo = 0;
+      zhi = c->slab.k1 - c->slab.e0; if (zhi > L.mz) zhi = L.mz;
+    }
+    for (int kz0 = zlo; kz0 < zhi; kz0 += chunk) {
+      const int kz1 = kz0 + chunk < zhi ? kz0 + chunk : zhi;
       for (int col = 0; col < 8; ++col) {
         const int ci = col & 1, cj = (col >> 1) & 1, ck = (col >> 2) & 1;
         const int kf = kz0 + (((kz0 & 1) != ck) ? 1 : 0);
