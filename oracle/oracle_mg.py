@@ -41,6 +41,72 @@ def interp_lattice(dims_c):
     return P.tocsr()
 
 
+def petsc_gmres(apply_A, apply_M, b, rtol=1e-5, atol=1e-50, dtol=1e4, max_it=10000, restart=30, side="left", flexible=False):
+    """KSPSolve_GMRES / KSPSolve_FGMRES from a zero initial guess (App. B.5): classical Gram-Schmidt in one pass, Givens QR
+    of the Hessenberg, residual estimate |g_{j+1}|, default convergence test rnorm <= max(rtol * rnorm0, atol).
+    side="left": iterates on M^-1 A and measures the preconditioned residual; "right" (and FGMRES): unpreconditioned.
+    Returns (x, its, reason, hist)."""
+    n = len(b); x = np.zeros(n); hist = []; its = 0; reason = 0; rnorm0 = None; ttol = 0.0
+    left = side == "left" and not flexible
+    while not reason:
+        r = b - apply_A(x) if its else b.copy()
+        if left:
+            r = apply_M(r)
+        res = np.linalg.norm(r)
+        if rnorm0 is None:
+            rnorm0 = res; ttol = max(rtol * rnorm0, atol)
+        if len(hist) == its:
+            hist.append(res)
+        if res == 0.0 or res <= ttol:
+            reason = 2 if res > 0.0 or rnorm0 > 0.0 else 3; break
+        if its >= max_it:
+            reason = -3; break
+        m = restart
+        V = np.zeros((m + 1, n)); Z = np.zeros((m, n)) if (flexible or not left) else None; H = np.zeros((m + 1, m))
+        V[0] = r / res
+        g = np.zeros(m + 1); g[0] = res; cs = np.zeros(m); sn = np.zeros(m); R = np.zeros((m + 1, m))
+        k = 0
+        for j in range(m):
+            if left:
+                w = apply_M(apply_A(V[j]))
+            else:
+                Z[j] = apply_M(V[j]); w = apply_A(Z[j])
+            h = V[:j + 1] @ w
+            w = w - V[:j + 1].T @ h
+            hn = np.linalg.norm(w)
+            H[:j + 1, j] = h; H[j + 1, j] = hn
+            if hn != 0.0:
+                V[j + 1] = w / hn
+            col = H[:j + 2, j].copy()
+            for i in range(j):
+                t = col[i]; col[i] = cs[i] * t + sn[i] * col[i + 1]; col[i + 1] = -sn[i] * t + cs[i] * col[i + 1]
+            tt = np.hypot(col[j], col[j + 1])
+            if tt == 0.0:
+                reason = -5; break
+            cs[j] = col[j] / tt; sn[j] = col[j + 1] / tt
+            g[j + 1] = -sn[j] * g[j]; g[j] = cs[j] * g[j]
+            col[j] = cs[j] * col[j] + sn[j] * col[j + 1]; col[j + 1] = 0.0
+            R[:j + 2, j] = col
+            res = abs(g[j + 1]); k = j + 1; its += 1
+            hist.append(res)
+            if res <= ttol:
+                reason = 2
+            elif res >= dtol * rnorm0:
+                reason = -4
+            elif its >= max_it:
+                reason = -3
+            elif hn == 0.0:
+                reason = 2      # happy breakdown
+            if reason:
+                break
+        if k:
+            y = np.zeros(k)
+            for i in range(k - 1, -1, -1):
+                y[i] = (g[i] - R[i, i + 1:k] @ y[i + 1:k]) / R[i, i]
+            x = x + (V[:k].T @ y if left else Z[:k].T @ y)
+    return x, its, reason, np.array(hist)
+
+
 class Level:
     pass
 
@@ -88,6 +154,18 @@ class MonolithicMG:
                 lv.P = sp.block_diag([Pu, interp_lattice(pd)], format="csr")
             self.levels[k] = lv
         self.lu = spla.splu(self.levels[0].A.tocsc())
+        self.fs_coarse = "fs_coarse" in o
+        if self.fs_coarse:   # exSaddle.c:366-398: FGMRES + fieldsplit Schur-upper (user Mpscaled_coarse) on the coarse level
+            for key, want in (("saddle_mg_coarse_ksp_type", "fgmres"), ("saddle_mg_coarse_fieldsplit_u_pc_type", "jacobi"),
+                              ("saddle_mg_coarse_fieldsplit_p_pc_type", "jacobi"), ("saddle_mg_coarse_ksp_convergence_test", "default")):
+                if o.get(key) != want:
+                    raise NotImplementedError("oracle -fs_coarse: the golden's tree only (-%s %s)" % (key, want))
+            c = probs[0]; lv0 = self.levels[0]; nu = c.nu
+            A = lv0.A
+            lv0.A00 = A[:nu, :nu].tocsr(); lv0.A01 = A[:nu, nu:].tocsr(); lv0.A10 = A[nu:, :nu].tocsr(); lv0.A11 = A[nu:, nu:].tocsr()
+            jac = lambda d: np.where(d == 0.0, 1.0, 1.0 / np.where(d == 0.0, 1.0, d))
+            lv0.id00 = jac(lv0.A00.diagonal()); lv0.idmp = jac(c.Mp().scipy().diagonal()); lv0.nu = nu
+            self.coarse_its = []
         self.fine = fine
         self.smooth_its = int(o.get("saddle_mg_levels_ksp_max_it", 2))   # PCMG default: 2 smoothing steps
         self.restart = int(o.get("saddle_mg_levels_ksp_gmres_restart", 30))
@@ -128,12 +206,27 @@ class MonolithicMG:
     def vcycle(self, l, b):
         lv = self.levels[l]
         if l == 0:
-            return self.lu.solve(b)
+            return self.coarse_fieldsplit(b) if self.fs_coarse else self.lu.solve(b)
         x = self.smooth(lv, b, np.zeros(lv.n), self.smooth_its)
         r = b - lv.A @ x
         xc = self.vcycle(l - 1, lv.P.T @ r)
         x = x + lv.P @ xc
         return self.smooth(lv, b, x, self.smooth_its)
+
+    # -- coarse solver of -fs_coarse: FGMRES(rtol 1e-5) with PCFIELDSPLIT Schur / UPPER / user Mpscaled_coarse (App. B.2):
+    #      y_p = GMRES[S, Jacobi(Mp)] x_p with S v = A11 v - A10 GMRES[A00, Jacobi](A01 v);  y_u = GMRES[A00, Jacobi](x_u - A01 y_p)
+    def coarse_fieldsplit(self, b):
+        L = self.levels[0]; nu = L.nu
+        ksp_u = lambda rhs: petsc_gmres(lambda v: L.A00 @ v, lambda v: L.id00 * v, rhs)[0]
+        S = lambda v: L.A11 @ v - L.A10 @ ksp_u(L.A01 @ v)
+
+        def pc(r):
+            yp = petsc_gmres(S, lambda v: L.idmp * v, r[nu:])[0]
+            yu = ksp_u(r[:nu] - L.A01 @ yp)
+            return np.concatenate([yu, yp])
+        x, its, reason, _ = petsc_gmres(lambda v: L.A @ v, pc, b, flexible=True)
+        self.coarse_its.append(its)
+        return x
 
     def pc_apply(self, r):
         return self.vcycle(len(self.levels) - 1, r)
@@ -141,8 +234,11 @@ class MonolithicMG:
     # -- KSPSolve_FGMRES, right PC, unpreconditioned norm (App. B.5)
     def solve(self, b=None):
         o = self.o
-        if o.get("saddle_ksp_type", "gmres") != "fgmres":
-            raise NotImplementedError("oracle -mg outer solver: fgmres")
+        if o.get("saddle_ksp_type", "gmres") != "fgmres":   # the default: GMRES, left PC, preconditioned norm (mg_fs_coarse_1.ref)
+            A = self.levels[-1].A
+            return petsc_gmres(lambda v: A @ v, self.pc_apply, self.fine.F() if b is None else b,
+                               rtol=float(o.get("saddle_ksp_rtol", 1e-5)), max_it=int(o.get("saddle_ksp_max_it", 10000)),
+                               restart=int(o.get("saddle_ksp_gmres_restart", 30)), side=o.get("saddle_ksp_pc_side", "left"))
         rtol = float(o.get("saddle_ksp_rtol", 1e-5)); atol = float(o.get("saddle_ksp_atol", 1e-50)); dtol = 1e4
         max_it = int(o.get("saddle_ksp_max_it", 10000)); m = int(o.get("saddle_ksp_gmres_restart", 30))
         A = self.levels[-1].A; n = A.shape[0]

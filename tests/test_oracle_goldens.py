@@ -378,3 +378,21 @@ def test_wavefront_window_of_the_pressure_ilu_sweeps():
             s = s * d                                        # the factor stores 1 / pivot (xo_ilu0)
             ring[(lvl & 7) * maxw + pos[r]] = s; x[r] = s
     assert not np.isnan(x).any() and np.linalg.norm(x - xs) <= 1e-13 * np.linalg.norm(xs)
+
+
+def test_monolithic_mg_fs_coarse_golden(kat):
+    """-mg -fs_coarse (exSaddle.c:366-398): outer GMRES (left PCMG, preconditioned norm), GMRES/Jacobi smoothers (2 steps), coarse
+    FGMRES preconditioned by PCFIELDSPLIT Schur / UPPER / user Mpscaled_coarse with GMRES + Jacobi on both splits and the nested
+    A00 solve inside every Schur-complement product (App. B.2; solver tree as printed by -saddle_ksp_view in the golden).
+    13 iterations and CONVERGED_RTOL as in testref/exSaddle3d_mg_fs_coarse_1.ref; residuals to 3e-5 (the nested inexact solves
+    at rtol 1e-5 amplify summation-order differences; the first six agree to all printed digits).  Oracle only: the product
+    rejects -fs_coarse with XSB_ERR_SUP."""
+    from oracle.oracle_mg import MonolithicMG
+    c = kat["exSaddle3d_mg_fs_coarse_1"]
+    M = MonolithicMG(c["options"], nsd=3)
+    x, its, reason, hist = M.solve()
+    assert (its, reason) == (c["iterations"], 2) and c["reason"] == "CONVERGED_RTOL" and len(hist) == len(c["residuals"])
+    assert [_short(v) for v in hist[:6]] == c["residuals_text"][:6]
+    assert np.allclose(hist, c["residuals"], rtol=3e-5, atol=0)
+    assert all(2 <= k <= 3 for k in M.coarse_its)       # the coarse FGMRES needs 2-3 iterations per V-cycle
+    assert M.fine.banner.rstrip("\n").split("\n") == c["banner"]
