@@ -396,3 +396,18 @@ def test_monolithic_mg_fs_coarse_golden(kat):
     assert np.allclose(hist, c["residuals"], rtol=3e-5, atol=0)
     assert all(2 <= k <= 3 for k in M.coarse_its)       # the coarse FGMRES needs 2-3 iterations per V-cycle
     assert M.fine.banner.rstrip("\n").split("\n") == c["banner"]
+
+
+# ---- the reference's plain -fs tree with PETSc's default sub-solvers (oracle only; oracle/oracle_fs.py) ----
+@pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1"])
+def test_plain_fs_tree_history_and_diagnostics_match_golden(kat, name):
+    """GMRES + PCFIELDSPLIT Schur / UPPER / user Mpscaled with GMRES + ILU(0) on both splits and the nested A00 solve inside every
+    Schur-complement product (App. B.2): residual history and diagnostics to every printed digit of testref/*_fs_1.ref."""
+    from oracle.oracle_fs import FieldSplitDefault
+    c = kat[name]
+    F = FieldSplitDefault(c["options"], nsd=c["nsd"], lame=c["lame"])
+    x, its, reason, hist = F.solve()
+    assert reason == 2 and its == len(c["residuals"]) - 1
+    assert [_short(v) for v in hist] == c["residuals_text"]
+    assert [g.rstrip() for g in F.p.diagnostics_text(x)] == [s.rstrip() for s in c["diagnostics"]]
+    assert F.p.banner.rstrip("\n").split("\n") == c["banner"]
