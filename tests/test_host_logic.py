@@ -200,3 +200,12 @@ def test_vts_writer_round_trip(tmp_path):
     assert np.array_equal(pts[node], np.stack([0.25 * i.ravel(), 0.5 * j.ravel(), 0.125 * k.ravel()], axis=1))
     head = open(path, "rb").read(400).decode(errors="replace")
     assert 'type="StructuredGrid"' in head and 'byte_order="LittleEndian"' in head and 'WholeExtent="0 4 0 2 0 3"' in head
+
+
+def test_bench_reference_arm_other_ranks_exit_without_work():
+    """Under torchrun (N > 1) rank 0 alone runs the CPU arm; the other ranks exit 0 and print nothing."""
+    import subprocess, sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], cwd=ROOT, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
