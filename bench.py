@@ -46,6 +46,15 @@ FP64_PEAK_TFLOPS = 36.72      # scripts/fp64_peak.cu on this pool's B200 (profil
 MF_FLOP_PER_ELEMENT = 7140.0  # FP64 flops the element kernel executes per element: 3 lanes x (927 DFMA x 2 + 418 DMUL + 108 DADD), cuobjdump -sass
 
 
+def a00_csr_bytes(mx, world=1):
+    """AIJ (CSR) bytes of one A00 product at mx^3, SURVEY 8d: 12 B/nnz + 4 B/row pointer + 16 B/row (x, y); the common yardstick
+    ("AIJ-equivalent GB/s") for the BAIJ and the matrix-free products.  nnz(A00) = 9 * (sum over a node line of its coupling width)^3."""
+    n1 = 2 * mx + 1
+    per_dir = sum(3 if (i % 2 or i in (0, n1 - 1)) else 5 for i in range(n1))
+    nnz = 9 * per_dir ** 3; rows = 3 * n1 ** 3
+    return (12.0 * nnz + 4.0 * (rows + 1) + 16.0 * rows) / world
+
+
 def timed_solves(g, torch, xdev, steps, barrier):
     """K solves, device-resident RHS, CUDA events on the handle's own stream; returns (ms, counters summed over the steps)."""
     stream = torch.cuda.ExternalStream(g.stream(), device=xdev.device)
@@ -295,7 +304,8 @@ def main():
                 "flops_per_launch": flops, "avg_launch_us": avg_apply_ns / 1e3, "launches_timed": n_applies,
                 "share_of_step": (n_applies * avg_apply_ns * 1e-9) / step_seconds,
                 "hbm_view": {"algorithmic_bytes": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world,
-                             "achieved_GBps": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world / max(avg_apply_ns, 1)}}
+                             "achieved_GBps": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world / max(avg_apply_ns, 1)},
+                "aij_equivalent_GBps": a00_csr_bytes(a.mx, world) / max(avg_apply_ns, 1)}
 
     # ---- full-A MatMult micro-measure (collective on slabs: every rank runs it): 10 warm-up + 30 timed applies.
     # Assembled path: the reference's MATAIJ layout; operator-free path: element kernel + A01 / A10 / A11 CSR products.
@@ -350,6 +360,7 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(("spmv_baij", a.mx, world)),
                     "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
                     "launches_timed": n_a00, "share_of_step": (n_a00 * avg_ns * 1e-9) / (sec_per_solve * a.steps),
+                    "aij_equivalent_GBps": a00_csr_bytes(a.mx, world) / max(avg_ns, 1),
                     "aij_matmult": {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)", "ms": aij_ms, "bytes": aij_bytes,
                                     "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak}}
         os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)

@@ -150,6 +150,7 @@ def test_bench_algorithmic_bytes_and_path_choice():
     bytes_plain = b.a00_bytes((3 * nun, 3 * nun, 9 * nblk, 3), [1, 0, 0, 0])
     assert abs(bytes_plain - 10.372e9) < 0.01e9
     assert b.a00_bytes((3 * nun, 3 * nun, 9 * nblk, 3), [0, 0, 0, 1]) > bytes_plain     # Chebyshev step streams 3 more vectors
+    assert abs(b.a00_csr_bytes(64) - 14.709e9) < 0.001e9 and abs(b.a00_csr_bytes(32) - 1.850e9) < 0.001e9   # A00 alone, AIJ layout
     # 32-bit PetscInt: the assembled operator needs nnz(A) per rank < 2^31 (5420 nnz per element at large m)
     assert 5420.0 * 64 ** 3 < 2.0e9 and 5420.0 * 128 ** 3 / 4 > 2.0e9 and 5420.0 * 128 ** 3 / 8 < 2.0e9
 
