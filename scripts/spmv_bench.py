@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import exsaddle_b200 as X
 mx = int(sys.argv[1]); reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-g = X.ExSaddle("-mx %d -model 6 -eta1 1e6" % mx, nsd=3).assemble()
+more = " " + sys.argv[3] if len(sys.argv) > 3 else ""      # e.g. "-xsb_baij_closed_form"
+g = X.ExSaddle("-mx %d -model 6 -eta1 1e6%s" % (mx, more), nsd=3).assemble()
 st = torch.cuda.ExternalStream(g.stream())
 peak = 6548.2
 out = {}
