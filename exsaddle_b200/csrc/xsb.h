@@ -177,9 +177,8 @@ struct xsb_ctx_s {
   double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr, *ilu_diag = nullptr; int ilu_nlvl = 0;
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
-  int ilu_kernel = 1, ilu_maxw = 0; unsigned short *ilu_fwin = nullptr, *ilu_bwin = nullptr;   // -xsb_ilu_kernel 2: windowed single-CTA solve (experimental)
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
-  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr; bool mf_l2_window = false, mf_fused_zero = false; bool baij_closed_form = false;   // -xsb_baij_closed_form (experimental)
+  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr;
   double *red = nullptr;      // device reduction scratch
   double *red_h = nullptr;    // pinned host mirror
   double *scal = nullptr;     // device scalars (dot results consumed by kernels)

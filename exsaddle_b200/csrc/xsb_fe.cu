@@ -615,7 +615,6 @@ int fe_assemble(xsb_ctx c)
   q1_interp_kernel<<<nblk(nq), 256, 0, st>>>(L, dT, c->coeff_nodal, c->coeff); KERNEL_OK();
   // operator-free mode (-xsb_matrix_free full): A and A00 are never stored (128^3: nnz(A) = 1.13e10 > 2^31 and 137 GB)
   { const std::string mfv = c->opt.str("xsb_matrix_free", "0"); c->no_A = (mfv == "full" || mfv == "2"); }
-  c->baij_closed_form = c->opt.flag("xsb_baij_closed_form");
   const bool split = c->no_A;
   if (split && nsd != 3) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free full is implemented for the 3-D executables");
   // AIJ pattern

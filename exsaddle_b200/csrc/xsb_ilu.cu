@@ -186,87 +186,6 @@ k_ilu0_solve(int nw, int np, const int *__restrict__ off, const int *__restrict_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Variant 2 (-xsb_ilu_kernel 2, EXPERIMENTAL: written without GPU time left in round 1, not yet measured; the default
-// stays the cluster kernel above).  A row of wavefront w only reads x of wavefronts w-7 .. w-1 (w = i + 2j + 4k on the
-// 27-point lattice), so ONE CTA can keep an 8-wavefront ring of x in shared memory: the per-wavefront cost becomes a
-// block barrier + a shared-memory FMA chain instead of a cluster barrier + an L2 round trip (2.7 us measured).  Columns
-// are replaced by 16-bit ring addresses ((w' & 7) * maxw + position inside wavefront w'), computed once at set-up.
-__global__ void k_ilu_rowpos(int np, const int *__restrict__ rows, int *rowpos)
-{ const int q = blockIdx.x * blockDim.x + threadIdx.x; if (q < np) rowpos[rows[q]] = q; }
-__global__ void k_ilu_window(int np, int maxw, const int *__restrict__ off, const int *__restrict__ lvl_of_q, const int *__restrict__ rowpos,
-                             const int *__restrict__ fcol, const int *__restrict__ bcol, unsigned short *fwin, unsigned short *bwin)
-{
-  const int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= np) return;
-  const int w = lvl_of_q[q], cnt = off[w + 1] - off[w], l = q - off[w];
-  const int64_t base = (int64_t)13 * off[w] + l;
-  for (int u = 0; u < 13; ++u) {
-    const int64_t idx = base + (int64_t)u * cnt;
-    int qq = rowpos[fcol[idx]], ww = lvl_of_q[qq]; fwin[idx] = (unsigned short)((ww & 7) * maxw + (qq - off[ww]));
-    qq = rowpos[bcol[idx]]; ww = lvl_of_q[qq]; bwin[idx] = (unsigned short)((ww & 7) * maxw + (qq - off[ww]));
-  }
-}
-
-#define ILUW_TPB 512
-struct IluRowW { double lv[13]; unsigned short wv[13]; int row, n; double aux, x0; };
-template <bool FWD>
-__device__ __forceinline__ void iluw_load(IluRowW &R, int o, int cnt, int l, const int *__restrict__ rows, const unsigned short *__restrict__ win,
-                                          const double *__restrict__ val, const unsigned char *__restrict__ nn, const double *__restrict__ aux, const double *xg)
-{
-  const int q = o + l; const int64_t base = (int64_t)13 * o + l;
-  R.row = rows[q]; R.n = nn[q];
-#pragma unroll
-  for (int u = 0; u < 13; ++u) { R.lv[u] = val[base + (int64_t)u * cnt]; R.wv[u] = win[base + (int64_t)u * cnt]; }
-  if (FWD) { R.aux = aux[R.row]; R.x0 = 0.0; } else { R.aux = aux[q]; R.x0 = __ldcg(xg + R.row); }   // backward: 1/pivot and the forward result
-}
-template <bool FWD>
-__device__ __forceinline__ void iluw_row(const IluRowW &R, double *ring, int slot, double *xg)
-{
-  double s = FWD ? R.aux : R.x0;
-#pragma unroll
-  for (int u = 0; u < 13; ++u) if (u < R.n) s -= R.lv[u] * ring[R.wv[u]];   // same column order as the sequential sweep
-  if (!FWD) s *= R.aux;
-  ring[slot] = s; __stcg(xg + R.row, s);
-}
-template <bool FWD>
-__device__ __forceinline__ void iluw_sweep(int nw, int maxw, const int *soff, double *ring, const int *__restrict__ rows, const unsigned short *__restrict__ win,
-                                           const double *__restrict__ val, const unsigned char *__restrict__ nn, const double *__restrict__ aux, double *xg)
-{
-  const int t = threadIdx.x;
-  const int wfirst = FWD ? 0 : nw - 1, wstep = FWD ? 1 : -1;
-  IluRowW cur, nxt;
-  bool have = t < soff[wfirst + 1] - soff[wfirst];
-  if (have) iluw_load<FWD>(cur, soff[wfirst], soff[wfirst + 1] - soff[wfirst], t, rows, win, val, nn, aux, xg);
-  for (int step = 0, w = wfirst; step < nw; ++step, w += wstep) {
-    const int o = soff[w], cnt = soff[w + 1] - o, wn = w + wstep;
-    bool have_next = false;
-    // the next wavefront's factors do not depend on x: load them before this wavefront's barrier.  (Backward: x0 = the forward
-    // result of that row, written in the forward sweep, which a __syncthreads() separates from this one.)
-    if (step + 1 < nw) { const int o1 = soff[wn], c1 = soff[wn + 1] - o1; have_next = t < c1; if (have_next) iluw_load<FWD>(nxt, o1, c1, t, rows, win, val, nn, aux, xg); }
-    if (have) iluw_row<FWD>(cur, ring, (w & 7) * maxw + t, xg);
-    for (int l = t + ILUW_TPB; l < cnt; l += ILUW_TPB) { IluRowW r; iluw_load<FWD>(r, o, cnt, l, rows, win, val, nn, aux, xg); iluw_row<FWD>(r, ring, (w & 7) * maxw + l, xg); }
-    __syncthreads();
-    cur = nxt; have = have_next;
-  }
-}
-__global__ void __launch_bounds__(ILUW_TPB) k_ilu0_solve_win(int nw, int np, int maxw, const int *__restrict__ off, const int *__restrict__ rows,
-                                                             const unsigned short *__restrict__ fwin, const double *__restrict__ fval, const unsigned char *__restrict__ fn,
-                                                             const unsigned short *__restrict__ bwin, const double *__restrict__ bval, const unsigned char *__restrict__ bn,
-                                                             const double *__restrict__ binv, const double *__restrict__ b, double *x)
-{
-  extern __shared__ double smw[];
-  double *ring = smw; int *soff = (int *)(ring + (size_t)8 * maxw);
-  for (int i = threadIdx.x; i <= nw; i += ILUW_TPB) soff[i] = off[i];
-  {   // L2 prefetch of the factor streams in sweep order (one SM pulls ~80 MB per apply)
-    const int64_t nv = (int64_t)13 * np;
-    for (int64_t i = (int64_t)threadIdx.x * 16; i < nv; i += (int64_t)ILUW_TPB * 16) prefetch_l2(fval + i);
-    for (int64_t i = (int64_t)threadIdx.x * 64; i < nv; i += (int64_t)ILUW_TPB * 64) prefetch_l2(fwin + i);
-  }
-  __syncthreads();
-  iluw_sweep<true>(nw, maxw, soff, ring, rows, fwin, fval, fn, b, x);
-  iluw_sweep<false>(nw, maxw, soff, ring, rows, bwin, bval, bn, binv, x);
-}
-
 // bjacobi block of this rank: rows and columns of the owned pressure planes [op0,op1) of the local lattice, as a
 // 27-point matrix on the owned sub-lattice (PETSc PCBJACOBI: the rank's diagonal block of Mpscaled).
 __global__ void k_own_len(PLat P, int *len)
@@ -339,22 +258,6 @@ int ilu_setup(xsb_ctx c)
     k_lvl_of_q<<<nw, 256, 0, st>>>(nw, c->ilu_lvl_off, lvl_of_q); KERNEL_OK();
     k_ilu_pack<<<(np + 255) / 256, 256, 0, st>>>(nw, c->ilu_lvl_off, c->ilu_rows, M.ia, M.ja, diag, c->mp_lu, lvl_of_q,
                                                    c->ilu_fcol, c->ilu_fval, c->ilu_fn, c->ilu_bcol, c->ilu_bval, c->ilu_bn, c->ilu_binv); KERNEL_OK();
-    // experimental single-CTA windowed solve (-xsb_ilu_kernel 2): ring addresses, if the 8-wavefront ring fits shared memory
-    c->ilu_kernel = c->opt.integer("xsb_ilu_kernel", 1); c->ilu_maxw = 0;
-    if (c->ilu_kernel == 2) {
-      std::vector<int> offh((size_t)nw + 1);
-      CUDA_OK(cudaMemcpyAsync(offh.data(), c->ilu_lvl_off, sizeof(int) * (nw + 1), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
-      int maxw = 0; for (int w = 0; w < nw; ++w) maxw = std::max(maxw, offh[w + 1] - offh[w]);
-      const size_t smem = sizeof(double) * 8 * (size_t)maxw + sizeof(int) * ((size_t)nw + 1);
-      if (8 * (size_t)maxw <= 65535 && smem <= 200 * 1024) {
-        int *rowpos = nullptr; XSB_CHK(dev_alloc(c, &rowpos, (size_t)np));
-        XSB_CHK(dev_alloc(c, &c->ilu_fwin, (size_t)13 * np + 64)); XSB_CHK(dev_alloc(c, &c->ilu_bwin, (size_t)13 * np + 64));
-        k_ilu_rowpos<<<(np + 255) / 256, 256, 0, st>>>(np, c->ilu_rows, rowpos); KERNEL_OK();
-        k_ilu_window<<<(np + 255) / 256, 256, 0, st>>>(np, maxw, c->ilu_lvl_off, lvl_of_q, rowpos, c->ilu_fcol, c->ilu_bcol, c->ilu_fwin, c->ilu_bwin); KERNEL_OK();
-        CUDA_OK(cudaFuncSetAttribute(k_ilu0_solve_win, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->ilu_maxw = maxw;
-      }   // else: the ring does not fit (128^3 on one GPU: 268 KB) -> cluster kernel
-    }
   }
   int h = 0; CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
   if (h) return xsb_fail(c, XSB_ERR_BREAKDOWN, "zero pivot in ILU(0) of Mpscaled");
@@ -363,12 +266,6 @@ int ilu_setup(xsb_ctx c)
 
 int ilu_apply(xsb_ctx c, const double *b, double *x)
 {
-  if (c->ilu_kernel == 2 && c->ilu_maxw > 0) {
-    const size_t smem = sizeof(double) * 8 * (size_t)c->ilu_maxw + sizeof(int) * ((size_t)c->ilu_nlvl + 1);
-    k_ilu0_solve_win<<<1, ILUW_TPB, smem, c->stream>>>(c->ilu_nlvl, c->MpOwn.n, c->ilu_maxw, c->ilu_lvl_off, c->ilu_rows, c->ilu_fwin, c->ilu_fval, c->ilu_fn,
-                                                      c->ilu_bwin, c->ilu_bval, c->ilu_bn, c->ilu_binv, b, x); KERNEL_OK();
-    return 0;
-  }
   k_ilu0_solve<<<ILU_CLUSTER, ILU_TPB, sizeof(int) * (c->ilu_nlvl + 1), c->stream>>>(c->ilu_nlvl, c->MpOwn.n, c->ilu_lvl_off, c->ilu_rows, c->ilu_fcol, c->ilu_fval, c->ilu_fn,
                                                        c->ilu_bcol, c->ilu_bval, c->ilu_bn, c->ilu_binv, b, x); KERNEL_OK();
   return 0;

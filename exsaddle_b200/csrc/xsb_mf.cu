@@ -291,15 +291,11 @@ __device__ __forceinline__ double mf_epi(const Epilogue &ep, int64_t i, double a
   }
 }
 // out = epilogue( isbc ? x : (K x) ): identity rows of the constrained dofs + the fused smoother update
-// ZERO (-xsb_mf_fused_zero, opt-in, not yet run on a GPU): the accumulator is zeroed as it is read, so the next product needs
-// no memset pass.  The default keeps the memset + read-only epilogue that every round-1 measurement and test ran with.
-template <bool ZERO>
 __global__ void mf_epilogue_kernel(int64_t n, const unsigned char *__restrict__ isbc, const double *__restrict__ x, double *kx,
                                    double *__restrict__ out, Epilogue ep)
 {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double v = kx[i];
-    if (ZERO) kx[i] = 0.0;
     if (isbc && isbc[i]) v = x[i];
     out[i] = mf_epi(ep, i, v);
   }
@@ -312,29 +308,9 @@ int mf_setup(xsb_ctx c)
   CUDA_OK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, c->stream));
   if (!c->mf_tmp) XSB_CHK(dev_alloc(c, &c->mf_tmp, (size_t)c->lat.nu));
   c->so.mf_kernel = c->opt.integer("xsb_mf_kernel", 3);   // 1: 9 lanes per element (v1); 2, 3: 3 lanes per element, preloaded / reduction scatter
-  { const bool want = c->opt.flag("xsb_mf_fused_zero");   // switching it on: the accumulator must be zero once
-    if (want && !c->mf_fused_zero) CUDA_OK(cudaMemsetAsync(c->mf_tmp, 0, sizeof(double) * c->lat.nu, c->stream));
-    c->mf_fused_zero = want; }
   c->so.mf_chunk = c->opt.integer("xsb_mf_chunk", 0);     // element layers per z-chunk (0 = no chunking)
   c->so.mf_reverse = c->opt.integer("xsb_mf_reverse", 1); // alternate the sweep direction of successive colour launches
   if (c->so.mf_kernel < 1 || c->so.mf_kernel > 3) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_kernel must be 1, 2 or 3");
-  if (c->opt.flag("xsb_mf_l2_persist") && !c->mf_l2_window) {
-    // EXPERIMENTAL (opt-in, not measured in round 1): pin the accumulator in L2 across the 8 colour passes of a product.
-    // ncu: every pass re-reads 56 % of x and of the accumulator from DRAM (72 MB per pass, 3.6 x the algorithmic traffic).
-    cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, c->device));
-    const size_t bytes = sizeof(double) * (size_t)c->lat.nu;
-    size_t setaside = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
-    size_t win = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
-    if (setaside > 0 && win > 0) {
-      CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside));
-      cudaStreamAttrValue v; memset(&v, 0, sizeof(v));
-      v.accessPolicyWindow.base_ptr = c->mf_tmp; v.accessPolicyWindow.num_bytes = win;
-      v.accessPolicyWindow.hitRatio = (float)((double)setaside / (double)win > 1.0 ? 1.0 : (double)setaside / (double)win);
-      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      CUDA_OK(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v));
-      c->mf_l2_window = true;
-    }
-  }
   if (!c->mf_bcnode) {
     XSB_CHK(dev_alloc(c, &c->mf_bcnode, (size_t)c->lat.nun));
     mf_bcnode_kernel<<<(unsigned)((c->lat.nun + 255) / 256), 256, 0, c->stream>>>(c->lat.nun, c->isbc, c->mf_bcnode); KERNEL_OK();
@@ -362,10 +338,7 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
   const Lattice &L = c->lat; cudaStream_t st = c->stream;
   const double detJ = L.hu[0] * L.hu[1] * L.hu[2];
   const double *eta = c->coeff;   // slot C_ETA (eta, or mu for LAME)
-  // the accumulator starts zero: memset per product (default), or left zero by the previous product's epilogue (opt-in; the
-  // first product after allocation finds dev_alloc's zero fill)
-  const bool fused_zero = c->mf_fused_zero;
-  if (!fused_zero) CUDA_OK(cudaMemsetAsync(c->mf_tmp, 0, sizeof(double) * L.nu, st));
+  CUDA_OK(cudaMemsetAsync(c->mf_tmp, 0, sizeof(double) * L.nu, st));
   MfTabS TS; { MfTab T0; host_mf_tab(T0);
     for (int q = 0; q < 3; ++q) { TS.w[q] = T0.w[q]; for (int n = 0; n < 3; ++n) { TS.N[q][n] = T0.N[q][n]; TS.Dx[q][n] = T0.D[q][n] / L.hu[0]; TS.Dy[q][n] = T0.D[q][n] / L.hu[1]; TS.Dz[q][n] = T0.D[q][n] / L.hu[2]; } } }
   if (c->so.mf_kernel == 1) {
@@ -405,8 +378,7 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
     }
   }
   int64_t nb = (L.nu + 255) / 256; if (nb > 148 * 16) nb = 148 * 16;
-  if (fused_zero) mf_epilogue_kernel<true><<<(unsigned)nb, 256, 0, st>>>(L.nu, isbc, x, c->mf_tmp, y, ep);
-  else mf_epilogue_kernel<false><<<(unsigned)nb, 256, 0, st>>>(L.nu, isbc, x, c->mf_tmp, y, ep);
+  mf_epilogue_kernel<<<(unsigned)nb, 256, 0, st>>>(L.nu, isbc, x, c->mf_tmp, y, ep);
   KERNEL_OK();
   return 0;
 }

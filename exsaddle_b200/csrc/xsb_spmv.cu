@@ -135,55 +135,6 @@ __global__ void __launch_bounds__(256) spmv_baij_kernel(int node0, int nb, const
   }
 }
 
-// EXPERIMENTAL variant (-xsb_baij_closed_form, off by default, not measured in round 1): the block columns of a box-pattern
-// matrix are a closed-form function of the row's node, so the 4 B/block index stream (5 % of the bytes of the BS = 3
-// product) need not be read.  Each lane walks its own slot sequence s = g, g + NBW, ... through the row's box incrementally
-// (no div/mod in the loop); everything else is the kernel above.
-template <int BS, int UN>
-__global__ void __launch_bounds__(256) spmv_baij_cf_kernel(int node0, int nb, BoxPattern pat, const int *__restrict__ ia,
-                                                           const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y, Epilogue ep)
-{
-  constexpr int BS2 = BS * BS, NBW = 32 / BS2, ACTIVE = NBW * BS2;
-  const int lane = threadIdx.x & 31;
-  const int g = lane / BS2, r = lane - g * BS2, ra = r / BS, ca = r - ra * BS;
-  const bool active = lane < ACTIVE;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int nxny = pat.nx * pat.ny;
-  for (int64_t node = node0 + warp; node < node0 + nb; node += nwarps) {
-    const int b0 = ia[node], nblk = ia[node + 1] - b0;
-    const double *__restrict__ av = a + (int64_t)b0 * BS2 + lane;
-    const int mine = active ? (nblk - g + NBW - 1) / NBW : 0;
-    // the row's box and this lane's first slot (g) inside it
-    const int i = (int)(node % pat.nx), j = (int)((node / pat.nx) % pat.ny), k = (int)(node / nxny);
-    int l0, h0, l1, h1, l2, h2; box_range(pat, i, pat.nx, l0, h0); box_range(pat, j, pat.ny, l1, h1); box_range(pat, k, pat.nz, l2, h2);
-    const int bx = h0 - l0 + 1, by = h1 - l1 + 1;
-    int ii = g % bx, jj = (g / bx) % by, kk = g / (bx * by);
-    int col = (l0 + ii) + (l1 + jj) * pat.nx + (l2 + kk) * nxny;
-    double acc = 0.0;
-    for (int it = 0; it < mine; it += UN) {
-      double v[UN]; int cidx[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const bool ok = it + u < mine;
-        v[u] = ok ? ld_stream(av + (int64_t)(it + u) * ACTIVE) : 0.0;
-        cidx[u] = ok ? col : 0;
-        // advance this lane's slot by NBW inside the box (NBW <= bx + ... : at most one wrap per direction for NBW <= 3 <= bx)
-        ii += NBW; col += NBW;
-        while (ii >= bx) { ii -= bx; col += pat.nx - bx; if (++jj >= by) { jj -= by; col += nxny - by * pat.nx; } }
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) acc += v[u] * __ldg(x + (int64_t)BS * cidx[u] + ca);
-    }
-    double t = acc;
-#pragma unroll
-    for (int s = 1; s < BS; ++s) t += __shfl_down_sync(0xffffffffu, acc, s);
-    double tot = t;
-#pragma unroll
-    for (int s = 1; s < NBW; ++s) tot += __shfl_down_sync(0xffffffffu, t, s * BS2);
-    if (g == 0 && ca == 0 && active) { const int64_t idx = (int64_t)BS * node + ra; y[idx] = epilogue_value(ep, idx, tot); }
-  }
-}
-
 int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0, int nnodes)
 {
   if (nnodes < 0) nnodes = A.nb - node0;
@@ -191,8 +142,7 @@ int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilog
   const int tpb = 256; int64_t blocks = ((int64_t)nnodes * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;
   if (blocks > cap) blocks = cap;
-  if (c->baij_closed_form && A.bs == 3 && A.pat.nx > 0) spmv_baij_cf_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.pat, A.ia, A.a, x, y, ep);
-  else if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
+  if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
   else if (A.bs == 2) spmv_baij_kernel<2, 4><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
   else return xsb_fail(c, XSB_ERR_SUP, "BAIJ block size %d", A.bs);
   KERNEL_OK();

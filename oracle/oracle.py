@@ -97,6 +97,8 @@ def lib():
         L.xo_rander48.argtypes = [C.c_int, C.c_int, dp]
         L.xo_hess_eig.argtypes = [C.c_int, dp, C.c_int, dp, dp]
         L.xo_num_threads.restype = C.c_int
+        L.xo_set_num_threads.argtypes = [C.c_int]
+        L.xo_set_sum_order.argtypes = [C.c_int]
         _lib = L
     return _lib
 

@@ -146,6 +146,8 @@ void xo_diagnostics(const xo_problem *p, const double *x, double *out /* 5*nsd +
 void xo_rander48(int n, int interval, double *v);          /* PETSc rander48 stream, seed 0x12345678 */
 int  xo_hess_eig(int n, const double *H, int ldh, double *re, double *im); /* eigenvalues of upper Hessenberg */
 int  xo_num_threads(void);
+void xo_set_num_threads(int n);   /* OpenMP team size (bench.py sets all host cores: torchrun exports OMP_NUM_THREADS=1) */
+void xo_set_sum_order(int o);     /* 0 reference order (default); 1 reversed dot-product / row sums: oracle-vs-oracle drift experiment */
 
 #ifdef __cplusplus
 }

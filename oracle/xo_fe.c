@@ -799,6 +799,15 @@ static void assemble(xo_problem *P)
 void xo_csr_mult(int n, const int *ia, const int *ja, const double *a, const double *x, double *y)
 {
   int i;
+  if (xo_sum_order == 1) {   /* drift experiment only: row sums from the last stored entry to the first */
+#pragma omp parallel for schedule(static)
+    for (i = 0; i < n; ++i) {
+      double s = 0.0; int k;
+      for (k = ia[i + 1] - 1; k >= ia[i]; --k) s += a[k] * x[ja[k]];
+      y[i] = s;
+    }
+    return;
+  }
 #pragma omp parallel for schedule(static)
   for (i = 0; i < n; ++i) {
     double s = 0.0; int k;

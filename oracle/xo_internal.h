@@ -72,6 +72,7 @@ struct xo_problem_s {
 
 static inline int xo_fail(xo_problem *P, const char *msg) { snprintf(P->err, sizeof(P->err), "%s", msg); return 1; }
 static inline double xo_wtime(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+extern int xo_sum_order;   /* 0 = reference order; 1 = reversed sums (drift experiment, xo_solve.c) */
 void xo_solver_free(xo_problem *P);
 const char *xo_error(const xo_problem *P);
 

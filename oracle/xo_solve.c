@@ -19,10 +19,29 @@ int xo_num_threads(void)
 #endif
 }
 
+void xo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ---------------------------------------------------------------- vectors */
+/* Summation-order switch (xo_set_sum_order; 0 = default).  1: dot products and matrix-row sums run from the last term to the
+   first.  Used only to measure how far a residual history moves when nothing but the floating-point summation order
+   changes (oracle-vs-oracle drift, scripts/oracle_drift.py); the reference's order is the default. */
+int xo_sum_order = 0;
+void xo_set_sum_order(int o) { xo_sum_order = o; }
 static double vdot(int64_t n, const double *x, const double *y)
 {
   double s = 0.0; int64_t i;
+  if (xo_sum_order == 1) {
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (i = n - 1; i >= 0; --i) s += x[i] * y[i];
+    return s;
+  }
 #pragma omp parallel for reduction(+ : s) schedule(static)
   for (i = 0; i < n; ++i) s += x[i] * y[i];
   return s;

@@ -456,42 +456,3 @@ def test_petsc_binary_dumps_of_operator_and_solution(tmp_path):
     s.close()
 
 
-# ------------------------------------------------------------------ experimental kernels (opt-in options, off by default)
-@pytest.mark.skipif(__import__("os").environ.get("XSB_EXPERIMENTAL") != "1", reason="experimental variants: set XSB_EXPERIMENTAL=1")
-@pytest.mark.parametrize("opts", ["-model 6 -mx 8 -eta1 1e4", "-model 1 -mx 4 -my 6 -mz 2", "-model 6 -mx 16 -eta1 100"])
-def test_experimental_windowed_ilu_matches_oracle(opts):
-    """-xsb_ilu_kernel 2 (single-CTA solve with an 8-wavefront ring of x in shared memory) against the oracle's sequential
-    forward / backward substitution, and against the default cluster kernel."""
-    full = "%s %s -saddle_fieldsplit_u_pc_mg_levels 2" % (ABF, opts)
-    g2 = X.ExSaddle(full + " -xsb_ilu_kernel 2", nsd=3).assemble().ksp_setup()
-    g1 = X.ExSaddle(full, nsd=3).assemble().ksp_setup()
-    o = O.Problem(full, nsd=3)
-    M = o.Mp(); lu = np.empty_like(M.a)
-    assert O.lib().xo_ilu0(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
-    rng = np.random.default_rng(13)
-    for _ in range(2):
-        bp = rng.standard_normal(o.np_)
-        xp = np.empty(o.np_); O.lib().xo_ilu0_solve(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(bp), O._dp(xp))
-        x2, x1 = g2.pc_schur_apply(bp), g1.pc_schur_apply(bp)
-        assert np.linalg.norm(x2 - xp) <= 1e-12 * np.linalg.norm(xp)
-        assert np.array_equal(x2, x1)      # same operations per row in the same order
-    g1.close(); g2.close()
-
-
-@pytest.mark.skipif(__import__("os").environ.get("XSB_EXPERIMENTAL") != "1", reason="experimental variants: set XSB_EXPERIMENTAL=1")
-@pytest.mark.parametrize("opts", ["-model 6 -mx 8 -eta1 1e4", "-model 1 -mx 4 -my 6 -mz 2", "-model 2 -mx 1", "-model 11 -size_x 0.1 -mx 6"])
-def test_experimental_closed_form_baij_is_bitwise_the_indexed_kernel(opts):
-    """-xsb_baij_closed_form: block columns from the box pattern instead of the ja stream; same products in the same order."""
-    levels = 2 if "-mx 1" not in opts else 1
-    full = "%s %s -saddle_fieldsplit_u_pc_mg_levels %d" % (ABF, opts, levels)
-    g2 = X.ExSaddle(full + " -xsb_baij_closed_form", nsd=3).assemble().ksp_setup()
-    g1 = X.ExSaddle(full, nsd=3).assemble().ksp_setup()
-    rng = np.random.default_rng(17)
-    x = rng.standard_normal(g1.nu)
-    assert np.array_equal(g2.mat_mult(X.MAT_A00, x), g1.mat_mult(X.MAT_A00, x))
-    for l in range(levels):
-        n = g1.mat_info(X.MAT_MG_LEVEL0 + l)[0]; xl = rng.standard_normal(n)
-        assert np.array_equal(g2.mat_mult(X.MAT_MG_LEVEL0 + l, xl), g1.mat_mult(X.MAT_MG_LEVEL0 + l, xl))
-    x1, x2 = g1.solve(), g2.solve()
-    assert g1.iterations() == g2.iterations() and np.array_equal(g1.history(), g2.history()) and np.array_equal(x1, x2)
-    g1.close(); g2.close()
