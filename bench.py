@@ -148,16 +148,25 @@ def a00_bytes(info, by_mode):
     return mat + 8 * rows * sum(vecs[m] * by_mode[m] for m in range(4)) / tot
 
 
-def cpu_reference(a, steps, warmup, emit):
-    """The reference's CPU implementation of the path.  PETSc is not installable here (no PETSc/MPI in the image),
-    so this is the oracle port (oracle/xo_*.c, OpenMP over all host cores), timed on a bounded sample: the first
-    `sample_outer` outer FGMRES iterations of the same system.  The sample is scaled to the full solve by operator
-    products, not by outer iterations: the first outer iterations run 7, 6, 2 inner GCR iterations against 1.45 on
-    average, and a GCR iteration is 17 fine-level A00 products.  cost = alpha * (n_A00 + 1.66 n_A), 1.66 = AIJ bytes of
-    the full operator / CSR bytes of A00; the full solve's counts come from the committed oracle fixture
-    (tests/golden/oracle_<mx>cubed_history.json: outer and inner iteration counts of the oracle's own full solve) or,
-    for other configurations, from the GPU arm's counters of the same configuration."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(a, full_solve):
+    """The reference's CPU implementation of the path.  PETSc is not installable here (no PETSc/MPI in the image), so this is
+    the oracle port (oracle/xo_*.c, OpenMP), on ALL host cores: the team size is set explicitly because torchrun exports
+    OMP_NUM_THREADS=1 (round 1's reference arm ran single-threaded under torchrun and timed out).
+
+    full_solve=True  (--impl reference): ONE complete solve of the workload, timed (exSaddle.c:569-599 protocol without the
+                     warm-up solve: a CPU solve has no launch/JIT warm-up to hide and one solve is minutes); value = its seconds.
+    full_solve=False (cpu_baseline of the GPU arm): a bounded sample -- the first `sample_outer` outer FGMRES iterations --
+                     scaled to the full solve by operator products (cost ~ n_A00 + 1.66 n_A; 1.66 = AIJ bytes of A / CSR bytes
+                     of A00), the full solve's counts taken from the committed oracle fixture.  Labelled as an estimate."""
     from oracle import oracle as O
+    O.lib().xo_set_num_threads(host_cores())
     cores = O.lib().xo_num_threads()
     opts = workload_options(a)
     t0 = time.time()
@@ -165,6 +174,14 @@ def cpu_reference(a, steps, warmup, emit):
     s = p.solver()
     p.pc_setup(s)
     t_setup = time.time() - t0
+    if full_solve:
+        x, res = p.solve(s)
+        value = res.solve_seconds if res.reason > 0 else None
+        base = {"value": value, "unit": "s", "cores": cores, "kind": "port",
+                "sample": "ONE complete solve of the same %d^3 system on the oracle port (OpenMP, %d threads): %d outer FGMRES iterations, %d inner GCR iterations, "
+                          "%d A00 + %d full-A products, converged reason %d; CPU set-up %.1f s not included" % (a.mx, cores, res.its, sum(res.inner_its[:res.n_inner]), res.n_a00_mult, res.n_a_mult, res.reason, t_setup),
+                "outer_its": int(res.its), "reason": int(res.reason), "steps_run": 1, "setup_s": t_setup}
+        return base
     full = None   # (outer its, A00 products, full-A products) of the complete solve
     fx = os.path.join(ROOT, "tests", "golden", "oracle_%dcubed_history.json" % a.mx)
     if os.path.exists(fx):
@@ -176,27 +193,21 @@ def cpu_reference(a, steps, warmup, emit):
         if e.get("outer_its"):
             full = (e["outer_its"], 17 * e.get("inner_its_total", 0), e["outer_its"] + 1 + e["outer_its"] // 30, "GPU arm's counters")
     s.max_outer_sample = max(1, a.sample_outer)
-    times = []
-    steps, warmup = min(steps, 2), min(warmup, 1)   # bounded: one sample is ~30 s of CPU at 64^3
-    for i in range(warmup + steps):
-        x, res = p.solve(s)
-        if i >= warmup:
-            times.append(res.solve_seconds)
-    t_sample = sum(times) / len(times)
+    x, res = p.solve(s)
+    t_sample = res.solve_seconds
     work = lambda n00, nA: n00 + 1.66 * nA
     w_sample = work(res.n_a00_mult, res.n_a_mult)
     if res.reason > 0:        # the sample converged: it IS the full solve
         value, how = t_sample, "complete solve (%d outer iterations)" % res.its
     elif full is not None and w_sample > 0:
         value = t_sample * work(full[1], full[2]) / w_sample
-        how = ("scaled by operator products to the full solve's %d outer / %d inner iterations = %d A00 + %d full-A products (%s)"
-               % (full[0], full[1] // 17, full[1], full[2], full[3]))
+        how = ("ESTIMATE: scaled by operator products to the full solve's %d outer / %d inner iterations = %d A00 + %d full-A products (%s); "
+               "the measured complete solve is what `bench.py --impl reference` reports" % (full[0], full[1] // 17, full[1], full[2], full[3]))
     else:
         value, how = None, "no iteration counts of the full solve available"
-    base = {"value": value, "unit": "s", "cores": cores, "kind": "port",
+    return {"value": value, "unit": "s", "cores": cores, "kind": "port", "estimated": res.reason <= 0,
             "sample": "first %d outer FGMRES iterations (%d A00 + %d full-A products, %.2f s) of the same %d^3 system on the oracle port (OpenMP, %d threads), %s; CPU set-up %.1f s not included"
                       % (res.its, res.n_a00_mult, res.n_a_mult, t_sample, a.mx, cores, how, t_setup)}
-    return base, t_sample, t_setup
 
 
 def main():
@@ -228,9 +239,10 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        base, per_outer, t_setup = cpu_reference(a, max(1, a.steps), a.warmup, None)
+        base = cpu_reference(a, True)
         line = {"impl": "reference", "metric": "stokes_ksp_solve_time_rtol1e-8", "value": base["value"], "unit": "s", "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": None if base["value"] is None else 1e3 * base["value"],
+                "steps": 1, "warmup": 0, "steps_requested": a.steps, "warmup_requested": a.warmup,
+                "ms_per_step": None if base["value"] is None else 1e3 * base["value"],
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -315,6 +327,7 @@ def main():
     xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
     yout = torch.empty_like(xin)
     stream = torch.cuda.ExternalStream(g.stream(), device=xdev.device)
+    stream.wait_stream(torch.cuda.current_stream())   # xin is produced on torch's stream, consumed on the library's
     with torch.cuda.stream(stream):
         for _ in range(10):
             g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
@@ -378,7 +391,7 @@ def main():
                 import psutil
                 need_gb = 45.0 * (a.mx / 64.0) ** 3
                 if psutil.virtual_memory().available / 2 ** 30 > need_gb + 8:
-                    base, _, _ = cpu_reference(a, 1, 0, None)
+                    base = cpu_reference(a, False)
                 else:
                     base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped: host RAM below %.0f GB" % need_gb}
             except Exception as e:   # the checker must never take the bench line down

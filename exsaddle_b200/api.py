@@ -54,6 +54,7 @@ def lib():
             "xsb_ksp_get_iterations": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "xsb_ksp_get_history": [vp, dp, C.c_int, C.POINTER(C.c_int)],
             "xsb_ksp_get_inner_iterations": [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)],
+            "xsb_ksp_get_inner_reasons": [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)],
             "xsb_ksp_get_chebyshev": [vp, C.c_int, dp, dp, dp, dp], "xsb_ksp_get_timing": [vp, dp, dp],
             "xsb_ksp_get_counters": [vp, i64p], "xsb_diagnostics": [vp, dp, dp], "xsb_get_stream": [vp, C.POINTER(vp)],
             "xsb_pattern_row": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, C.c_int],
@@ -289,6 +290,11 @@ class ExSaddle:
     def inner_iterations(self):
         n = C.c_int(); a = (C.c_int * 20000)()
         self._chk(self.L.xsb_ksp_get_inner_iterations(self.h, a, 20000, C.byref(n)))
+        return [a[i] for i in range(n.value)]
+
+    def inner_reasons(self):
+        n = C.c_int(); a = (C.c_int * 20000)()
+        self._chk(self.L.xsb_ksp_get_inner_reasons(self.h, a, 20000, C.byref(n)))
         return [a[i] for i in range(n.value)]
 
     def chebyshev(self, level):

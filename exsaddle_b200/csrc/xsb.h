@@ -106,6 +106,9 @@ struct FeTables {
   double detJ;              // h_x h_y (h_z)
 };
 
+// 1-D Q2 basis / derivative tables of the element kernels: N[q][n], Dd[q][n] = D[q][n] / h_d (uniform mesh: J = diag(h))
+struct MfTabS { double N[3][3], Dx[3][3], Dy[3][3], Dz[3][3], w[3]; };
+
 struct Csr  { int n = 0, m = 0; int64_t nnz = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; };
 // BAIJ: block rows = lattice nodes, blocks bs x bs stored row-major, block columns ascending.
 struct Baij { int nb = 0, bs = 0; int64_t nblk = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; BoxPattern pat{0, 0, 0, 0}; };
@@ -178,12 +181,13 @@ struct xsb_ctx_s {
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
-  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr;
+  double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr, *mf_bczero = nullptr; bool mf_opts_read = false;
+  double *mf_part = nullptr; int *mf_zitems = nullptr; int mf_nz = 0, mf_zkey[3] = {-1, -1, -1}, mf_sms = 0; bool mf_ready = false;   // one-pass element kernel: partial sums of shared nodes, z-boundary list
   double *red = nullptr;      // device reduction scratch
   double *red_h = nullptr;    // pinned host mirror
   double *scal = nullptr;     // device scalars (dot results consumed by kernels)
   // results
-  int its = 0, reason = 0; std::vector<double> hist; std::vector<int> inner_its;
+  int its = 0, reason = 0; std::vector<double> hist; std::vector<int> inner_its, inner_reason;
   float setup_ms = 0, solve_ms = 0;
   int64_t n_a00 = 0, n_a = 0, n_launch = 0, solve_launches = 0; double a00_ns_sum = 0; int64_t a00_timed = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
@@ -192,6 +196,7 @@ struct xsb_ctx_s {
   Slab slab; void *nccl = nullptr;          // ncclComm_t when nranks > 1
   Ranges own_full, own_u, own_p;            // owned entries of [u|p], u and p vectors on the local lattice
   std::vector<void *> allocs;   // every device allocation, for xsb_reset
+  std::vector<char> alloc_phase; int phase = 0;   // 0: xsb_assemble, 1: xsb_ksp_setup (freed when the solver is set up again), 2: lazily created element-kernel state
   void *fe_tables = nullptr;    // FeTables on the device
   void *mmg = nullptr;          // monolithic -mg hierarchy (xsb_mmg.cu)
   const double *nodal_in = nullptr;   // coarse -mg level: nodal Q1 coefficient fields [slot][p-node] to use instead of the model
@@ -204,6 +209,8 @@ int xsb_fail(xsb_ctx c, int code, const char *fmt, ...);
 
 template <class T> int dev_alloc(xsb_ctx c, T **p, size_t n);
 int dev_free_all(xsb_ctx c);
+int dev_free(xsb_ctx c, void *p);          // one allocation made by dev_alloc
+int dev_free_phase(xsb_ctx c, int phase);  // every allocation of one phase
 
 // ---- xsb_fe.cu
 int fe_resolve_model(xsb_ctx c);
@@ -220,6 +227,10 @@ int spmv_collect_timing(xsb_ctx c);
 int mf_setup(xsb_ctx c);
 int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep);
 int mf_a00_apply_raw(xsb_ctx c, const double *x, double *y);   // without the Dirichlet rows / columns (A before MatZeroRowsColumns)
+void mf_tab_scaled(const Lattice &L, MfTabS &T);
+// ---- xsb_mf1p.cu (one-pass, TMA-staged element kernel)
+int mf1p_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep, const unsigned char *bcnode, int zlo, int zhi);
+int mf1p_partition(int P, int64_t ncols, int nl, int p, int64_t *lo, int64_t *hi);   // host mirror of the kernel's work split (tests)
 // ---- xsb_mfull.cu (operator-free mode)
 int mf_diag_inv(xsb_ctx c, double *idiag);                    // 1 / diag(A00) from the element matrices
 int galerkin_elements(xsb_ctx c, Level &C);                   // P^T A00 P assembled element by element on the local lattice
@@ -271,6 +282,8 @@ int ilu_apply(xsb_ctx c, const double *b, double *x);
 int ksp_setup(xsb_ctx c);
 int op_full_mult(xsb_ctx c, const double *x, double *y);
 int ksp_solve(xsb_ctx c, const double *b_dev, double *x_dev);
-int pc_apply(xsb_ctx c, const double *r, double *z, int *inner);
+int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reason = nullptr);
 int hess_eig(int n, const double *H, int ldh, double *wr, double *wi);
 int csr_diag_inv(xsb_ctx c, const Csr &A, double *idiag);
+int csr_diag(xsb_ctx c, const Csr &A, double *diag);
+int baij_diag(xsb_ctx c, const Baij &A, double *diag);

@@ -15,10 +15,10 @@ int xsb_fail(xsb_ctx c, int code, const char *fmt, ...)
 template <class T> int dev_alloc(xsb_ctx c, T **p, size_t n)
 {
   void *q = nullptr; if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 32);   // + slack: 16-byte granular bulk copies may touch the granule holding the last value
   if (e != cudaSuccess) return xsb_fail(c, XSB_ERR_MEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
   cudaMemsetAsync(q, 0, n * sizeof(T), c->stream);   // ghost entries of slab vectors must be finite
-  c->allocs.push_back(q); *p = (T *)q;
+  c->allocs.push_back(q); c->alloc_phase.push_back((char)c->phase); *p = (T *)q;
   return 0;
 }
 template int dev_alloc<double>(xsb_ctx, double **, size_t);
@@ -30,7 +30,24 @@ template int dev_alloc<unsigned short>(xsb_ctx, unsigned short **, size_t);
 int dev_free_all(xsb_ctx c)
 {
   for (void *p : c->allocs) cudaFree(p);
-  c->allocs.clear();
+  c->allocs.clear(); c->alloc_phase.clear();
+  return 0;
+}
+int dev_free(xsb_ctx c, void *p)
+{
+  if (!p) return 0;
+  for (size_t i = 0; i < c->allocs.size(); ++i) if (c->allocs[i] == p) { c->allocs.erase(c->allocs.begin() + i); c->alloc_phase.erase(c->alloc_phase.begin() + i); break; }
+  cudaFree(p);
+  return 0;
+}
+int dev_free_phase(xsb_ctx c, int phase)
+{
+  size_t k = 0;
+  for (size_t i = 0; i < c->allocs.size(); ++i) {
+    if (c->alloc_phase[i] == phase) cudaFree(c->allocs[i]);
+    else { c->allocs[k] = c->allocs[i]; c->alloc_phase[k] = c->alloc_phase[i]; ++k; }
+  }
+  c->allocs.resize(k); c->alloc_phase.resize(k);
   return 0;
 }
 
@@ -103,7 +120,7 @@ int xsb_set_option(xsb_ctx c, const char *key, const char *value)
   if (k.empty()) return xsb_fail(c, XSB_ERR_ARG, "empty option name");
   if (k == "options_file") return xsb_set_options_file(c, value ? value : "");
   c->opt.kv[k] = value ? value : "";
-  c->ksp_ready = false;
+  c->ksp_ready = false; c->mf_opts_read = false;
   return XSB_OK;
 }
 
@@ -261,11 +278,13 @@ int xsb_mat_mult_transpose(xsb_ctx c, int which, const double *x, double *y)
 int xsb_mat_get_diagonal(xsb_ctx c, int which, double *d)
 {
   NEED_DEVICE(c);
-  int64_t rows, cols, nnz; XSB_CHK(xsb_mat_get_info(c, which, &rows, &cols, &nnz, nullptr));
-  std::vector<int32_t> ia(rows + 1), ja(nnz); std::vector<double> a(nnz);
-  XSB_CHK(xsb_mat_get_csr(c, which, ia.data(), ja.data(), a.data()));
-  for (int64_t i = 0; i < rows; ++i) { d[i] = 0.0; for (int k = ia[i]; k < ia[i + 1]; ++k) if (ja[k] == i) d[i] = a[k]; }
-  return XSB_OK;
+  const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
+  const int64_t rows = S ? S->n : (int64_t)B->nb * B->bs;
+  double *dd = nullptr; CUDA_OK(cudaMalloc(&dd, sizeof(double) * rows));
+  int rc = S ? csr_diag(c, *S, dd) : baij_diag(c, *B, dd);   // read on the device: one pass over the matrix, only the diagonal crosses PCIe
+  if (!rc) { cudaError_t e = cudaMemcpyAsync(d, dd, sizeof(double) * rows, cudaMemcpyDeviceToHost, c->stream); if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); if (e != cudaSuccess) rc = xsb_fail(c, XSB_ERR_CUDA, "%s", cudaGetErrorString(e)); }
+  cudaFree(dd);
+  return rc;
 }
 
 int xsb_vec_get_rhs(xsb_ctx c, double *F)
@@ -345,7 +364,7 @@ int xsb_pc_schur_apply(xsb_ctx c, const double *b, double *x)
   NEED_DEVICE(c);
   if (!c->ksp_ready || c->so.pc_type != 2) return xsb_fail(c, XSB_ERR_ORDER, "fieldsplit PC not set up");
   return staged(c, c->lat.np, c->lat.np, b, x, [](xsb_ctx cc, const double *a, double *bb) {
-    if (cc->so.p_pc == 0) return ilu_apply(cc, a, bb);
+    if (cc->so.p_pc == 0) return ilu_apply(cc, a + cc->own_p.off0, bb + cc->own_p.off0);   // bjacobi: this rank's block acts on its owned rows
     return vec_pmult(cc, cc->lat.np, cc->mp_idiag, a, bb); });
 }
 
@@ -392,6 +411,13 @@ int xsb_ksp_get_inner_iterations(xsb_ctx c, int *its, int cap, int *n)
   if (!c) return XSB_ERR_ARG;
   int m = (int)c->inner_its.size(); if (n) *n = m;
   for (int i = 0; i < m && i < cap; ++i) its[i] = c->inner_its[i];
+  return XSB_OK;
+}
+int xsb_ksp_get_inner_reasons(xsb_ctx c, int *reasons, int cap, int *n)
+{
+  if (!c) return XSB_ERR_ARG;
+  int m = (int)c->inner_reason.size(); if (n) *n = m;
+  for (int i = 0; i < m && i < cap; ++i) reasons[i] = c->inner_reason[i];
   return XSB_OK;
 }
 int xsb_ksp_get_chebyshev(xsb_ctx c, int level, double *emin_est, double *emax_est, double *emin, double *emax)

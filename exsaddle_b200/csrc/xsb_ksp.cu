@@ -60,7 +60,6 @@ int op_full_mult(xsb_ctx c, const double *x, double *y)
 {
   if (c->no_A) {   // operator-free: y_u = A00 x_u (element kernel) + A01 x_p ; y_p = A11 x_p + A10 x_u
     const Lattice &L = c->lat; Epilogue ep;
-    XSB_CHK(mf_setup(c));
     XSB_CHK(comm_halo_full(c, const_cast<double *>(x)));
     XSB_CHK(mf_a00_apply(c, x, y, ep));
     XSB_CHK(spmv_csr(c, c->A01, x + L.nu, y, c->own_u.off0, c->own_u.len0, y));
@@ -76,7 +75,7 @@ static int full_mult(xsb_ctx c, const double *x, double *y) { c->n_a++; return o
 static int a00_mult(xsb_ctx c, const double *x, double *y) { Epilogue ep; return spmv_a00_fine(c, c->A00, x, y, ep); }
 
 // ------------------------------------------------------------------ KSPSolve_GCR on A00, right PC = PCMG
-static int gcr_solve(xsb_ctx c, const double *b, double *x, int *its_out)
+static int gcr_solve(xsb_ctx c, const double *b, double *x, int *its_out, int *reason_out)
 {
   const SolverOpts &s = c->so; const int64_t n = c->lat.nu; const int m = s.u_restart;
   double *r = c->gcr_r, *dots = c->scal;     // dots[0..m) mdot results, dots[64] r.v, dots[65] v.v, dots[66] ||r||^2
@@ -88,10 +87,11 @@ static int gcr_solve(xsb_ctx c, const double *b, double *x, int *its_out)
   XSB_CHK(vec_mdot(c, rg, r, nullptr, 0, true, dots + 66));
   XSB_CHK(vec_fetch(c, dots + 66, 1, h));
   const double rnorm0 = sqrt(h[0]), ttol = fmax(s.u_rtol * rnorm0, 1e-50);
-  if (rnorm0 <= ttol) { *its_out = 0; return 0; }
+  int reason = 0;
+  if (rnorm0 <= ttol) { *its_out = 0; if (reason_out) *reason_out = 3; return 0; }
   while (!done && its < s.u_max_it) {
     for (int k = 0; k < m; ++k) {
-      if ((int)c->GV.size() <= k) { double *v = nullptr, *sv = nullptr; XSB_CHK(dev_alloc(c, &v, (size_t)n)); XSB_CHK(dev_alloc(c, &sv, (size_t)n)); c->GV.push_back(v); c->GS.push_back(sv); }
+      if ((int)c->GV.size() <= k) { double *v = nullptr, *sv = nullptr; c->phase = 1; int rc = dev_alloc(c, &v, (size_t)n); if (!rc) rc = dev_alloc(c, &sv, (size_t)n); c->phase = 0; if (rc) return rc; c->GV.push_back(v); c->GS.push_back(sv); }
       double *v = c->GV[k], *sv = c->GS[k];
       XSB_CHK(mg_vcycle(c, r, sv));                                   // s = B^-1 r
       XSB_CHK(a00_mult(c, sv, v));                                    // v = A s
@@ -105,15 +105,16 @@ static int gcr_solve(xsb_ctx c, const double *b, double *x, int *its_out)
       XSB_CHK(vec_fetch(c, dots + 66, 1, h));
       const double norm_r = sqrt(h[0]);
       its++;
-      if (norm_r <= ttol || norm_r >= 1e4 * rnorm0 || its >= s.u_max_it) { done = true; break; }
+      if (norm_r <= ttol) reason = 2; else if (norm_r >= 1e4 * rnorm0) reason = -4; else if (its >= s.u_max_it) reason = -3;   // KSPConvergedDefault order
+      if (reason) { done = true; break; }
     }
   }
-  *its_out = its;
+  *its_out = its; if (reason_out) *reason_out = reason ? reason : -3;
   return 0;
 }
 
 // ------------------------------------------------------------------ PCApply
-int pc_apply(xsb_ctx c, const double *r, double *z, int *inner)
+int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reason)
 {
   const Lattice &L = c->lat;
   if (inner) *inner = 0;
@@ -126,9 +127,10 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner)
   XSB_CHK(comm_halo_p(c, yp));
   XSB_CHK(spmv_csr(c, c->A01, yp, c->fs_tu, c->own_u.off0, c->own_u.len0));
   XSB_CHK(vec_aypx(c, L.nu, -1.0, r, c->fs_tu));      // t_u = x_u - A01 y_p
-  int its = 0;
-  XSB_CHK(gcr_solve(c, c->fs_tu, z, &its));
+  int its = 0, why = 0;
+  XSB_CHK(gcr_solve(c, c->fs_tu, z, &its, &why));
   if (inner) *inner = its;
+  if (inner_reason) *inner_reason = why;
   return 0;
 }
 
@@ -154,6 +156,9 @@ static int read_solver_options(xsb_ctx c)
       return xsb_fail(c, XSB_ERR_SUP, "MG smoother must be chebyshev/jacobi");
     o.has("saddle_fieldsplit_u_pc_mg_galerkin"); o.has("saddle_fieldsplit_u_mg_levels_ksp_norm_type"); o.has("saddle_fieldsplit_u_mg_coarse_pc_factor_mat_solver_type");
   } else {
+    // the reference sets no PC type here (exSaddle.c:303-402 only does for -fs / -mg), so PETSc's default applies: ilu on one
+    // rank, bjacobi + ilu on several.  That default is not implemented: say so instead of silently running unpreconditioned.
+    if (!o.has("saddle_pc_type")) return xsb_fail(c, XSB_ERR_SUP, "no -saddle_pc_type given: PETSc's default (ilu / bjacobi+ilu on the saddle matrix) is not implemented; pass -saddle_pc_type jacobi|none, -fs or -mg");
     const std::string pc = o.str("saddle_pc_type", "none");
     if (pc == "jacobi") s.pc_type = 1; else if (pc == "none") s.pc_type = 0;
     else return xsb_fail(c, XSB_ERR_SUP, "-saddle_pc_type %s not supported without -fs (jacobi|none)", pc.c_str());
@@ -172,6 +177,8 @@ static int read_solver_options(xsb_ctx c)
     for (int i = 0; i < 4; ++i) s.esteig[i] = v[i];
   }
   s.esteig_steps = o.integer("saddle_fieldsplit_u_mg_levels_ksp_chebyshev_esteig_steps", 10);
+  if (s.esteig_steps < 1 || s.esteig_steps > 60) return xsb_fail(c, XSB_ERR_ARG, "-..._ksp_chebyshev_esteig_steps must be in [1,60]");   // the dot-product scratch holds 128 scalars
+  if (s.pc_type == 2 && s.cheb_its < 1) return xsb_fail(c, XSB_ERR_ARG, "-saddle_fieldsplit_u_mg_levels_ksp_max_it must be >= 1");
   s.noise = o.integer("xsb_chebyshev_noise", 0);
   s.n_cheb_fixed = 0;
   for (int l = 1; l < s.mg_levels; ++l) {
@@ -204,9 +211,23 @@ int ksp_setup(xsb_ctx c)
   if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_ksp_setup called before xsb_assemble");
   XSB_CHK(read_solver_options(c));
   const Lattice &L = c->lat;
+  // Re-entry (an option changed since the last set-up): everything the previous set-up allocated -- MG hierarchy, Galerkin
+  // levels, ILU factors, Krylov bases, work vectors -- is released first; the assembled operator (phase 0) stays.
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  mmg_free(c);
+  dev_free_phase(c, 1);
+  c->red = c->scal = nullptr; c->w_t1 = c->w_t2 = c->xdev = c->bdev = c->idiagA = c->gcr_r = c->fs_tu = nullptr;
+  c->mp_lu = c->mp_idiag = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
+  c->ilu_fval = c->ilu_bval = c->ilu_binv = nullptr; c->ilu_fn = c->ilu_bn = nullptr; c->MpOwn = Csr();
+  c->V.clear(); c->Z.clear(); c->GV.clear(); c->GS.clear();
+  for (int l = 0; l < XSB_MAX_LEVELS; ++l) c->lev[l] = Level();
+  c->nlev = 0;
+  c->phase = 1;
+  struct PhaseGuard { xsb_ctx c; ~PhaseGuard() { c->phase = 0; } } guard{c};
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
-  if (!c->red) { XSB_CHK(dev_alloc(c, &c->red, (size_t)592 * 8)); XSB_CHK(dev_alloc(c, &c->scal, 256)); CUDA_OK(cudaMallocHost(&c->red_h, sizeof(double) * 256)); }
-  if (!c->w_t1) { XSB_CHK(dev_alloc(c, &c->w_t1, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->w_t2, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->xdev, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->bdev, (size_t)L.n)); }
+  XSB_CHK(dev_alloc(c, &c->red, (size_t)592 * 8)); XSB_CHK(dev_alloc(c, &c->scal, 256));
+  if (!c->red_h) CUDA_OK(cudaMallocHost(&c->red_h, sizeof(double) * 256));
+  XSB_CHK(dev_alloc(c, &c->w_t1, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->w_t2, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->xdev, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->bdev, (size_t)L.n));
   if (c->so.pc_type == 1) { XSB_CHK(dev_alloc(c, &c->idiagA, (size_t)L.n)); XSB_CHK(csr_diag_inv(c, c->A, c->idiagA)); }
   if (c->so.pc_type == 3) XSB_CHK(mmg_setup(c));
   if (c->so.pc_type == 2) {
@@ -231,10 +252,10 @@ int ksp_solve(xsb_ctx c, const double *b, double *x)
   if (flex && !haspc) return xsb_fail(c, XSB_ERR_SUP, "fgmres without a preconditioner");
   std::vector<double> hh((size_t)(m + 1) * m), cs(m + 1), sn(m + 1), rs(m + 1), y(m + 1), hcol(m + 2);
   double *t1 = c->w_t1, *t2 = c->w_t2;
-  c->its = 0; c->reason = 0; c->hist.clear(); c->inner_its.clear();
+  c->its = 0; c->reason = 0; c->hist.clear(); c->inner_its.clear(); c->inner_reason.clear();
   c->n_a00 = c->n_a = 0; c->a00_ns_sum = 0; c->a00_timed = 0; c->ev_used = 0; for (int i = 0; i < 4; ++i) c->a00_mode[i] = 0;
   const int64_t launch0 = c->n_launch;
-  auto need = [&](std::vector<double *> &W, int k) -> int { while ((int)W.size() <= k) { double *p = nullptr; XSB_CHK(dev_alloc(c, &p, (size_t)n)); W.push_back(p); } return 0; };
+  auto need = [&](std::vector<double *> &W, int k) -> int { while ((int)W.size() <= k) { double *p = nullptr; c->phase = 1; int rc = dev_alloc(c, &p, (size_t)n); c->phase = 0; if (rc) return rc; W.push_back(p); } return 0; };
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   if (!b) b = c->F;
   XSB_CHK(vec_set(c, n, 0.0, x));          // initial guess is zero
@@ -263,8 +284,8 @@ int ksp_solve(xsb_ctx c, const double *b, double *x)
       double *w = c->V[it + 1];
       if (flex) {   // z_j = M^-1 v_j ; w = A z_j
         XSB_CHK(need(c->Z, it));
-        int inner = 0; XSB_CHK(pc_apply(c, c->V[it], c->Z[it], &inner));
-        if (s.pc_type == 2) c->inner_its.push_back(inner);
+        int inner = 0, why = 0; XSB_CHK(pc_apply(c, c->V[it], c->Z[it], &inner, &why));
+        if (s.pc_type == 2) { c->inner_its.push_back(inner); c->inner_reason.push_back(why); }
         XSB_CHK(full_mult(c, c->Z[it], w));
       } else if (right) {
         if (haspc) { XSB_CHK(pc_apply(c, c->V[it], t2, nullptr)); XSB_CHK(full_mult(c, t2, w)); } else XSB_CHK(full_mult(c, c->V[it], w));

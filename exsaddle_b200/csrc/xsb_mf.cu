@@ -29,6 +29,12 @@ static void host_mf_tab(MfTab &T)
   }
 }
 
+void mf_tab_scaled(const Lattice &L, MfTabS &TS)
+{
+  MfTab T0; host_mf_tab(T0);
+  for (int q = 0; q < 3; ++q) { TS.w[q] = T0.w[q]; for (int n = 0; n < 3; ++n) { TS.N[q][n] = T0.N[q][n]; TS.Dx[q][n] = T0.D[q][n] / L.hu[0]; TS.Dy[q][n] = T0.D[q][n] / L.hu[1]; TS.Dz[q][n] = T0.D[q][n] / L.hu[2]; } }
+}
+
 #define FULL 0xffffffffu
 // values of `v` held by the 3 lanes of my row (same b, a = 0,1,2) / my column (same a, b = 0,1,2)
 #define ROW3(v, o) { o[0] = __shfl_sync(FULL, v, rowb); o[1] = __shfl_sync(FULL, v, rowb + 1); o[2] = __shfl_sync(FULL, v, rowb + 2); }
@@ -135,7 +141,6 @@ __global__ void __launch_bounds__(128) mf_a00_kernel(Lattice L, int colour, doub
 // up front and unconditionally (27 x values, 9 per-node constraint masks, 9 viscosities), constraints are applied
 // with selects, and the scatter either preloads its 27 y values before the Gauss-point work (SCATTER 1) or uses
 // fire-and-forget reductions (SCATTER 0; one add per address per launch, so still deterministic).
-struct MfTabS { double N[3][3], Dx[3][3], Dy[3][3], Dz[3][3], w[3]; };   // Dd = D / h_d (uniform mesh: J = diag(h))
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 // (c,d) -> slot of the symmetric 3x3: xx yy zz xy xz yz
 __device__ __forceinline__ constexpr int sym_idx(int c, int d) { return c == d ? c : (c + d == 1 ? 3 : (c + d == 2 ? 4 : 5)); }
@@ -304,17 +309,21 @@ __global__ void mf_epilogue_kernel(int64_t n, const unsigned char *__restrict__ 
 int mf_setup(xsb_ctx c)
 {
   if (c->nsd != 3) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free is implemented for the 3-D Q2 velocity block");
+  if (c->mf_opts_read && c->mf_tmp && c->mf_bcnode) return 0;   // once per option change, not per product
+  const int keep_phase = c->phase; c->phase = 2;
+  struct PhaseGuard { xsb_ctx c; int p; ~PhaseGuard() { c->phase = p; } } guard{c, keep_phase};
   MfTab T; host_mf_tab(T);
   CUDA_OK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, c->stream));
   if (!c->mf_tmp) XSB_CHK(dev_alloc(c, &c->mf_tmp, (size_t)c->lat.nu));
-  c->so.mf_kernel = c->opt.integer("xsb_mf_kernel", 3);   // 1: 9 lanes per element (v1); 2, 3: 3 lanes per element, preloaded / reduction scatter
+  c->so.mf_kernel = c->opt.integer("xsb_mf_kernel", 4);   // 4: one-pass TMA-staged kernel (xsb_mf1p.cu); 1: 9 lanes per element, 8 colour passes; 2, 3: 3 lanes per element, preloaded / reduction scatter
   c->so.mf_chunk = c->opt.integer("xsb_mf_chunk", 0);     // element layers per z-chunk (0 = no chunking)
   c->so.mf_reverse = c->opt.integer("xsb_mf_reverse", 1); // alternate the sweep direction of successive colour launches
-  if (c->so.mf_kernel < 1 || c->so.mf_kernel > 3) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_kernel must be 1, 2 or 3");
+  if (c->so.mf_kernel < 1 || c->so.mf_kernel > 4) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_kernel must be 1 .. 4");
   if (!c->mf_bcnode) {
     XSB_CHK(dev_alloc(c, &c->mf_bcnode, (size_t)c->lat.nun));
     mf_bcnode_kernel<<<(unsigned)((c->lat.nun + 255) / 256), 256, 0, c->stream>>>(c->lat.nun, c->isbc, c->mf_bcnode); KERNEL_OK();
   }
+  c->mf_opts_read = true;
   return 0;
 }
 
@@ -325,12 +334,10 @@ int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep) { re
 int mf_a00_apply_raw(xsb_ctx c, const double *x, double *y)
 {
   XSB_CHK(mf_setup(c));
-  unsigned char *zero = nullptr; CUDA_OK(cudaMalloc(&zero, (size_t)c->lat.nun));
-  CUDA_OK(cudaMemsetAsync(zero, 0, (size_t)c->lat.nun, c->stream));
+  if (!c->mf_bczero) { const int kp = c->phase; c->phase = 2; int rc = dev_alloc(c, &c->mf_bczero, (size_t)c->lat.nun); c->phase = kp; if (rc) return rc; }   // dev_alloc zero-fills
   Epilogue ep; const int keep = c->so.mf_kernel; if (c->so.mf_kernel == 1) c->so.mf_kernel = 3;   // v1 reads the per-dof mask
-  int rc = mf_apply_core(c, x, y, ep, nullptr, zero);
+  int rc = mf_apply_core(c, x, y, ep, nullptr, c->mf_bczero);
   c->so.mf_kernel = keep;
-  cudaStreamSynchronize(c->stream); cudaFree(zero);
   return rc;
 }
 static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &ep, const unsigned char *isbc, const unsigned char *bcnode)
@@ -338,9 +345,20 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
   const Lattice &L = c->lat; cudaStream_t st = c->stream;
   const double detJ = L.hu[0] * L.hu[1] * L.hu[2];
   const double *eta = c->coeff;   // slot C_ETA (eta, or mu for LAME)
+  // Slabs: only the element layers that touch an owned node plane are needed, [k0-1, k1) of the local [k0-2, k1+1); the two
+  // extra ghost layers exist for the assembled Galerkin rows.
+  int zlo = 0, zhi = L.mz;
+  if (c->slab.nranks > 1 && isbc) {
+    zlo = c->slab.k0 - c->slab.e0 - 1; if (zlo < 0) zlo = 0;
+    zhi = c->slab.k1 - c->slab.e0; if (zhi > L.mz) zhi = L.mz;
+  }
+  if (c->so.mf_kernel == 4) {
+    const uintptr_t al = (uintptr_t)x | (uintptr_t)ep.b | (uintptr_t)ep.idiag | (uintptr_t)ep.pkm1;
+    if (al & 15) return xsb_fail(c, XSB_ERR_ARG, "one-pass element kernel: vectors must be 16-byte aligned");
+    return mf1p_apply(c, x, y, ep, bcnode, zlo, zhi);
+  }
   CUDA_OK(cudaMemsetAsync(c->mf_tmp, 0, sizeof(double) * L.nu, st));
-  MfTabS TS; { MfTab T0; host_mf_tab(T0);
-    for (int q = 0; q < 3; ++q) { TS.w[q] = T0.w[q]; for (int n = 0; n < 3; ++n) { TS.N[q][n] = T0.N[q][n]; TS.Dx[q][n] = T0.D[q][n] / L.hu[0]; TS.Dy[q][n] = T0.D[q][n] / L.hu[1]; TS.Dz[q][n] = T0.D[q][n] / L.hu[2]; } } }
+  MfTabS TS; mf_tab_scaled(L, TS);
   if (c->so.mf_kernel == 1) {
     for (int col = 0; col < 8; ++col) {
       const int ci = col & 1, cj = (col >> 1) & 1, ck = (col >> 2) & 1;
@@ -355,13 +373,6 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
     if (chunk <= 0) chunk = L.mz;
     if (chunk >= L.mz) chunk = L.mz; else chunk &= ~1;   // even chunk starts keep the colour parity pattern regular
     int launch = 0;
-    // Slabs: only the element layers that touch an owned node plane are needed, [k0-1, k1) of the local [k0-2, k1+1); the two
-    // extra ghost layers exist for the assembled Galerkin rows.  EXPERIMENTAL, opt-in (-xsb_mf_owned_layers): not yet run on >1 GPU.
-    int zlo = 0, zhi = L.mz;
-    if (c->slab.nranks > 1 && isbc && c->opt.flag("xsb_mf_owned_layers")) {
-      zlo = c->slab.k0 - c->slab.e0 - 1; if (zlo < 0) zlo = 0;
-      zhi = c->slab.k1 - c->slab.e0; if (zhi > L.mz) zhi = L.mz;
-    }
     for (int kz0 = zlo; kz0 < zhi; kz0 += chunk) {
       const int kz1 = kz0 + chunk < zhi ? kz0 + chunk : zhi;
       for (int col = 0; col < 8; ++col) {

@@ -218,6 +218,7 @@ static int galerkin_replicate(xsb_ctx c, const Level &F, Level &C)
   offs[S.nranks] = gia[ncn] * bs2;
   XSB_CHK(comm_bcast_segments(c, A.a, offs.data()));
   CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(len));
+  dev_free(c, T.A.ia); dev_free(c, T.A.ja); dev_free(c, T.A.a);   // the local product was only the source of the owned rows
   C.owns_A = true;
   return 0;
 }
@@ -244,6 +245,28 @@ __global__ void k_csr_idiag(int n, const int *__restrict__ ia, const int *__rest
   double v = 0.0; for (int k = ia[i]; k < ia[i + 1]; ++k) if (ja[k] == i) v = a[k];
   idiag[i] = v == 0.0 ? 1.0 : 1.0 / v;
 }
+template <int BS>
+__global__ void k_baij_diag(BoxPattern p, const int *__restrict__ ia, const double *__restrict__ a, double *__restrict__ diag)
+{
+  int64_t nd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (nd >= (int64_t)p.nx * p.ny * p.nz) return;
+  const int i = (int)(nd % p.nx), j = (int)((nd / p.nx) % p.ny), k = (int)(nd / ((int64_t)p.nx * p.ny));
+  const double *blk = a + (int64_t)(ia[nd] + box_slot(p, i, j, k, i, j, k)) * BS * BS;
+  for (int d = 0; d < BS; ++d) diag[BS * nd + d] = blk[d * BS + d];
+}
+__global__ void k_csr_diag(int n, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, double *__restrict__ diag)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  double v = 0.0; for (int k = ia[i]; k < ia[i + 1]; ++k) if (ja[k] == i) v = a[k];
+  diag[i] = v;
+}
+// MatGetDiagonal on the device
+int baij_diag(xsb_ctx c, const Baij &A, double *diag)
+{
+  if (A.bs == 3) k_baij_diag<3><<<nblk(A.nb), 256, 0, c->stream>>>(A.pat, A.ia, A.a, diag);
+  else k_baij_diag<2><<<nblk(A.nb), 256, 0, c->stream>>>(A.pat, A.ia, A.a, diag);
+  KERNEL_OK(); return 0;
+}
+int csr_diag(xsb_ctx c, const Csr &A, double *diag) { k_csr_diag<<<nblk(A.n), 256, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, diag); KERNEL_OK(); return 0; }
 int csr_diag_inv(xsb_ctx c, const Csr &A, double *idiag) { k_csr_idiag<<<nblk(A.n), 256, 0, c->stream>>>(A.n, A.ia, A.ja, A.a, idiag); KERNEL_OK(); return 0; }
 
 // BAIJ -> scalar CSR on the host (MatGetRowIJ view of a level operator; used by tests / xsb_mat_get_csr)
@@ -466,6 +489,8 @@ static int cheb_estimate(xsb_ctx c, Level &L)
   for (int i = 1; i < it; ++i) { if (wr[i] < L.emin_est) L.emin_est = wr[i]; if (wr[i] > L.emax_est) L.emax_est = wr[i]; }
   L.emin = s.esteig[0] * L.emin_est + s.esteig[1] * L.emax_est;
   L.emax = s.esteig[2] * L.emin_est + s.esteig[3] * L.emax_est;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (auto &v : V) dev_free(c, v);   // the Arnoldi basis is set-up scratch (11 fine-level vectors: 4.5 GB at 128^3)
   return 0;
 }
 

@@ -51,11 +51,12 @@ def run_exsaddle(exe, options, options_file_dir=None, outdir="."):
     its, reason = s.iterations()
     if "-saddle_ksp_monitor_short" in toks:
         out.append("  Residual norms for saddle_ solve.")
-        inner = s.inner_iterations()
+        inner, why = s.inner_iterations(), s.inner_reasons()
         show_inner = "-saddle_fieldsplit_u_ksp_converged_reason" in toks
         for i, r in enumerate(s.history()):
             if show_inner and i > 0 and i - 1 < len(inner):
-                out.append("  Linear saddle_fieldsplit_u_ solve converged due to CONVERGED_RTOL iterations %d" % inner[i - 1])
+                w = why[i - 1] if i - 1 < len(why) else 2
+                out.append("  Linear saddle_fieldsplit_u_ solve %s due to %s iterations %d" % ("converged" if w > 0 else "did not converge", _REASON.get(w, str(w)), inner[i - 1]))
             out.append("%3d KSP Residual norm %s " % (i, monitor_short(r)))
     if "-saddle_ksp_converged_reason" in toks:
         if reason > 0:

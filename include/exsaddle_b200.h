@@ -105,6 +105,7 @@ int xsb_mg_interpolate_add(xsb_ctx ctx, int coarse_level, const double *xc, doub
 int xsb_ksp_get_iterations(xsb_ctx ctx, int *its, int *reason);
 int xsb_ksp_get_history(xsb_ctx ctx, double *hist, int cap, int *n);
 int xsb_ksp_get_inner_iterations(xsb_ctx ctx, int *its, int cap, int *n);     /* fieldsplit_u GCR counts */
+int xsb_ksp_get_inner_reasons(xsb_ctx ctx, int *reasons, int cap, int *n);    /* KSPConvergedReason of each fieldsplit_u solve (-saddle_fieldsplit_u_ksp_converged_reason) */
 int xsb_ksp_get_chebyshev(xsb_ctx ctx, int level, double *emin_est, double *emax_est, double *emin, double *emax);
 int xsb_ksp_get_timing(xsb_ctx ctx, double *setup_ms, double *solve_ms);      /* CUDA-event times */
 /* KSPView / PCView (pc->ops->view, pcildl.c:429-456; -saddle_ksp_view): the solver tree in use, level sizes, nonzeros and

@@ -8,7 +8,7 @@ mx = int(sys.argv[1]); reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 more = " " + sys.argv[3] if len(sys.argv) > 3 else ""
 out = {}
 ref = None
-for name, which, extra in (("A00_baij", X.MAT_A00, ""), ("A00_mf_v1", X.MAT_A00_MF, " -xsb_mf_kernel 1"), ("A00_mf_v2", X.MAT_A00_MF, " -xsb_mf_kernel 2"), ("A00_mf_v3", X.MAT_A00_MF, " -xsb_mf_kernel 3")):
+for name, which, extra in (("A00_baij", X.MAT_A00, ""), ("A00_mf_v3", X.MAT_A00_MF, " -xsb_mf_kernel 3"), ("A00_mf_onepass", X.MAT_A00_MF, " -xsb_mf_kernel 4")):
     g = X.ExSaddle("-mx %d -model 6 -eta1 1e6%s%s" % (mx, extra, more), nsd=3).assemble()
     st = torch.cuda.ExternalStream(g.stream())
     rows = g.mat_info(X.MAT_A00)[0]

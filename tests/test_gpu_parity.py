@@ -268,8 +268,9 @@ def test_32cubed_properties():
 # ------------------------------------------------------------------ K4: matrix-free Q2 apply
 @pytest.mark.parametrize("opts,lame", [("-model 6 -mx 4 -eta1 1e4", False), ("-model 1 -mx 3 -my 5 -mz 2 -eta1 10", False),
                                        ("-model 11 -size_x 0.1 -mx 6", False), ("-model 0 -mx 5 -size_z 0.3 -freesliphack", False),
-                                       ("-model 12 -mx 4 -mu1 10", True), ("-model 2 -mx 1", False)])
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+                                       ("-model 12 -mx 4 -mu1 10", True), ("-model 2 -mx 1", False),
+                                       ("-model 6 -mx 18 -my 7 -mz 3 -eta1 1e3", False), ("-model 1 -mx 35 -my 11 -mz 2", False)])   # several tiles of the one-pass kernel
+@pytest.mark.parametrize("kernel", [3, 4])
 def test_matrix_free_apply_matches_assembled_block(opts, lame, kernel):
     g = X.ExSaddle(opts + " -xsb_mf_kernel %d" % kernel, nsd=3, lame=lame).assemble()
     o = O.Problem(opts, nsd=3, lame=lame)
@@ -280,6 +281,7 @@ def test_matrix_free_apply_matches_assembled_block(opts, lame, kernel):
         yo = A00 @ x
         assert np.linalg.norm(y - yo) <= 1e-12 * np.linalg.norm(yo)
         assert np.linalg.norm(y - g.mat_mult(X.MAT_A00, x)) <= 1e-12 * np.linalg.norm(yo)
+        assert np.array_equal(y, g.mat_mult(X.MAT_A00_MF, x))      # fixed summation order: bit-reproducible
     g.close()
 
 
