@@ -47,7 +47,7 @@ def lib():
             "xsb_view_fields": [vp, dp, C.c_char_p, C.c_char_p],
             "xsb_write_vts": [C.c_char_p, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(C.c_char_p), dp, C.c_int64, C.c_int64],
             "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
-            "xsb_ksp_setup": [vp], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
+            "xsb_ksp_setup": [vp], "xsb_ksp_reset": [vp], "xsb_get_state": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
             "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
             "xsb_pc_schur_apply": [vp, dp, dp], "xsb_mg_restrict": [vp, C.c_int, dp, dp],
             "xsb_mg_interpolate_add": [vp, C.c_int, dp, dp],

@@ -280,6 +280,7 @@ int ilu_setup(xsb_ctx c);
 int ilu_apply(xsb_ctx c, const double *b, double *x);
 // ---- xsb_ksp.cu
 int ksp_setup(xsb_ctx c);
+int ksp_release(xsb_ctx c);
 int op_full_mult(xsb_ctx c, const double *x, double *y);
 int ksp_solve(xsb_ctx c, const double *b_dev, double *x_dev);
 int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reason = nullptr);

@@ -318,6 +318,16 @@ int xsb_get_coeff_qp(xsb_ctx c, int slot, double *out)
 
 // ---------------------------------------------------------------- solver
 int xsb_ksp_setup(xsb_ctx c) { NEED_DEVICE(c); return ksp_setup(c); }
+int xsb_ksp_reset(xsb_ctx c)
+{
+  if (!c) return XSB_ERR_ARG;
+  c->ksp_ready = false;
+  if (!c->have_device) return XSB_OK;
+  cudaSetDevice(c->device);
+  return ksp_release(c);
+}
+int xsb_get_state(xsb_ctx c, int *assembled, int *ksp_ready)
+{ if (!c) return XSB_ERR_ARG; if (assembled) *assembled = c->assembled ? 1 : 0; if (ksp_ready) *ksp_ready = c->ksp_ready ? 1 : 0; return XSB_OK; }
 
 int xsb_ksp_solve_dev(xsb_ctx c, const double *b, double *x) { NEED_DEVICE(c); return ksp_solve(c, b, x); }
 

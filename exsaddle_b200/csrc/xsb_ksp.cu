@@ -206,13 +206,10 @@ static int read_solver_options(xsb_ctx c)
   return 0;
 }
 
-int ksp_setup(xsb_ctx c)
+// Releases everything xsb_ksp_setup and the solves allocated (phase-1 allocations): MG hierarchy, Galerkin levels, ILU
+// factors, Krylov bases, work vectors.  The assembled operator (phase 0) and the element-kernel state (phase 2) stay.
+int ksp_release(xsb_ctx c)
 {
-  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_ksp_setup called before xsb_assemble");
-  XSB_CHK(read_solver_options(c));
-  const Lattice &L = c->lat;
-  // Re-entry (an option changed since the last set-up): everything the previous set-up allocated -- MG hierarchy, Galerkin
-  // levels, ILU factors, Krylov bases, work vectors -- is released first; the assembled operator (phase 0) stays.
   CUDA_OK(cudaStreamSynchronize(c->stream));
   mmg_free(c);
   dev_free_phase(c, 1);
@@ -221,7 +218,17 @@ int ksp_setup(xsb_ctx c)
   c->ilu_fval = c->ilu_bval = c->ilu_binv = nullptr; c->ilu_fn = c->ilu_bn = nullptr; c->MpOwn = Csr();
   c->V.clear(); c->Z.clear(); c->GV.clear(); c->GS.clear();
   for (int l = 0; l < XSB_MAX_LEVELS; ++l) c->lev[l] = Level();
-  c->nlev = 0;
+  c->nlev = 0; c->ksp_ready = false;
+  return 0;
+}
+
+int ksp_setup(xsb_ctx c)
+{
+  if (!c->assembled) return xsb_fail(c, XSB_ERR_ORDER, "xsb_ksp_setup called before xsb_assemble");
+  XSB_CHK(read_solver_options(c));
+  const Lattice &L = c->lat;
+  // Re-entry (an option changed since the last set-up): everything the previous set-up allocated is released first
+  XSB_CHK(ksp_release(c));
   c->phase = 1;
   struct PhaseGuard { xsb_ctx c; ~PhaseGuard() { c->phase = 0; } } guard{c};
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));

@@ -92,6 +92,9 @@ int xsb_get_coeff_qp(xsb_ctx ctx, int slot /* 0 eta|mu 1 Fu0 2 Fu1 3 Fu2 4 Fp 5 
    Solver tree from the -saddle_* options: gmres|fgmres, pc jacobi | fieldsplit(Schur,UPPER,user Mpscaled)
    with fieldsplit_u = gcr + mg(Galerkin, chebyshev/jacobi, LU coarse), fieldsplit_p = preonly + bjacobi/ilu(0). */
 int xsb_ksp_setup(xsb_ctx ctx);
+int xsb_ksp_reset(xsb_ctx ctx);    /* PCReset_X (pcildl.c:376-394) of a PC that shares the handle with the Mat: frees the solver state
+                                      (MG hierarchy, ILU factors, Krylov bases), keeps the assembled operator and the options; idempotent */
+int xsb_get_state(xsb_ctx ctx, int *assembled, int *ksp_ready);
 int xsb_ksp_solve(xsb_ctx ctx, const double *b /* host, NULL = assembled F */, double *x /* host out */);
 int xsb_ksp_solve_dev(xsb_ctx ctx, const double *b /* device, NULL = F */, double *x /* device out */);
 int xsb_pc_apply(xsb_ctx ctx, const double *r, double *z);        /* PCApply of the outer PC, host pointers */
