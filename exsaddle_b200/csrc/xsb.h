@@ -150,6 +150,7 @@ struct SolverOpts {
   int n_cheb_fixed = 0; double cheb_emin[XSB_MAX_LEVELS], cheb_emax[XSB_MAX_LEVELS];
   int p_pc = 0;          // 0 ilu0 (bjacobi) 1 jacobi
   int time_kernels = 0;
+  int mf_tile = 0;       // -xsb_mf_tile: tile variant of the one-pass element kernel (0: 16 x 5 elements, one CTA per SM; 1: 8 x 5, two CTAs per SM)
   int mf_kernel = 3;     // -xsb_mf_kernel: 1 = 9 lanes per element, 2 / 3 = 3 lanes per element with preloaded / reduction scatter (xsb_mf.cu)
   int mf_reverse = 1;    // -xsb_mf_reverse: successive colour launches sweep the mesh in alternating directions (L2 reuse)
   int mf_chunk = 0;      // -xsb_mf_chunk: element layers per z-chunk of the matrix-free apply (0 = sized for L2)
@@ -177,12 +178,18 @@ struct xsb_ctx_s {
   double *idiagA = nullptr;
   // solver state
   int nlev = 0; Level lev[XSB_MAX_LEVELS];
+  int nsub = 0; Level sub[XSB_MAX_LEVELS];   // internal hierarchy below a coarsest level too large for the dense inverse (sub[nsub-1] aliases lev[0])
+  double *cg_p = nullptr, *cg_q = nullptr; int coarse_its = 0, coarse_solves = 0;
+  // V-cycle as a CUDA graph (-xsb_graph, default on): one captured graph per buffer-rotation state of the smoothers
+  struct VGraph { const double *b = nullptr; double *x = nullptr, *w0 = nullptr, *w1 = nullptr; cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr;
+                  int64_t d_a00 = 0, d_launch = 0, d_mode[4] = {0, 0, 0, 0}; double *px[XSB_MAX_LEVELS], *pw0[XSB_MAX_LEVELS], *pw1[XSB_MAX_LEVELS]; };
+  std::vector<VGraph> vgraphs; int use_graph = 1; int64_t graph_replays = 0;
   double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr, *ilu_diag = nullptr; int ilu_nlvl = 0;
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
   double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr, *mf_bczero = nullptr; bool mf_opts_read = false;
-  double *mf_part = nullptr; int *mf_zitems = nullptr; int mf_nz = 0, mf_zkey[3] = {-1, -1, -1}, mf_sms = 0; bool mf_ready = false;   // one-pass element kernel: partial sums of shared nodes, z-boundary list
+  double *mf_part = nullptr; int *mf_zitems = nullptr; int mf_nz = 0, mf_zkey[3] = {-1, -1, -1}, mf_sms = 0, mf_ready = 0;   // one-pass element kernel: partial sums of shared nodes, z-boundary list
   double *red = nullptr;      // device reduction scratch
   double *red_h = nullptr;    // pinned host mirror
   double *scal = nullptr;     // device scalars (dot results consumed by kernels)
@@ -230,6 +237,7 @@ int mf_a00_apply_raw(xsb_ctx c, const double *x, double *y);   // without the Di
 void mf_tab_scaled(const Lattice &L, MfTabS &T);
 // ---- xsb_mf1p.cu (one-pass, TMA-staged element kernel)
 int mf1p_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep, const unsigned char *bcnode, int zlo, int zhi);
+int mf1p_prepare(xsb_ctx c, int zlo, int zhi);   // allocations / tables of the kernel, outside any graph capture
 int mf1p_partition(int P, int64_t ncols, int nl, int p, int64_t *lo, int64_t *hi);   // host mirror of the kernel's work split (tests)
 // ---- xsb_mfull.cu (operator-free mode)
 int mf_diag_inv(xsb_ctx c, double *idiag);                    // 1 / diag(A00) from the element matrices
@@ -242,7 +250,7 @@ int vec_aypx(xsb_ctx c, int64_t n, double a, const double *x, double *y);       
 int vec_scale(xsb_ctx c, int64_t n, double a, double *x);
 int vec_pmult(xsb_ctx c, int64_t n, const double *d, const double *x, double *y);    // y = d .* x
 int vec_waxpy(xsb_ctx c, int64_t n, double a, const double *x, const double *y, double *w); // w = y + a x
-int vec_mdot(xsb_ctx c, const Ranges &rg, const double *w, double *const *V, int k, bool with_norm, double *out_dev); // out[j] = w.V[j], out[k] = w.w (owned entries, all ranks)
+int vec_mdot(xsb_ctx c, const Ranges &rg, const double *w, double *const *V, int k, bool with_norm, double *out_dev, bool local = false); // out[j] = w.V[j], out[k] = w.w (owned entries, all ranks; local: this rank's sum only, for replicated vectors)
 int vec_maxpy_dev(xsb_ctx c, int64_t n, double *w, double *const *V, int k, const double *coef_dev, double sign); // w += sign * sum coef[j] V[j]
 int vec_maxpy_host(xsb_ctx c, int64_t n, double *w, double *const *V, int k, const double *coef_host);
 int vec_scale_by_inv_sqrt(xsb_ctx c, int64_t n, double *w, const double *nrm2_dev);  // w /= sqrt(*nrm2)
@@ -265,6 +273,7 @@ inline Ranges whole(int64_t n) { Ranges r; r.len0 = n; return r; }
 // ---- xsb_mg.cu
 int mg_setup(xsb_ctx c);
 int mg_vcycle(xsb_ctx c, const double *b, double *x);
+void mg_graphs_release(xsb_ctx c);
 int mg_restrict(xsb_ctx c, const Level &F, const Level &C, const double *rf, double *bc);
 int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, double *xf);
 int baij_to_csr_host(xsb_ctx c, const Baij &A, int32_t *ia, int32_t *ja, double *a);

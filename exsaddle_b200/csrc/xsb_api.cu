@@ -81,7 +81,7 @@ int xsb_create(xsb_ctx *out, int nsd, int lame, int device)
 int xsb_reset(xsb_ctx c)
 {
   if (!c) return XSB_ERR_ARG;
-  if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); mmg_free(c); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
+  if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); mg_graphs_release(c); mmg_free(c); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
   Options opt = c->opt; int nsd = c->nsd, lame = c->lame, device = c->device; bool hd = c->have_device;
   const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl;
   cudaStream_t st = c->stream; cudaEvent_t e0 = c->ev0, e1 = c->ev1, k0 = c->evk0, k1 = c->evk1;
@@ -459,7 +459,8 @@ int xsb_ksp_view(xsb_ctx c, char *buf, int buflen)
     add("      fine-level products: %s\n", c->no_A ? "operator-free (sum-factorised Q2 element kernel; A and A00 not stored)" : s.matrix_free ? "matrix-free element kernel (A00 also assembled)" : "assembled BAIJ");
     for (int l = 0; l < c->nlev; ++l) {
       const Level &L = c->lev[l]; const long long rows = (long long)L.A.nb * L.A.bs, nz = (long long)L.A.nblk * L.A.bs * L.A.bs;
-      if (l == 0) add("      level 0 (coarse): preonly + lu (dense inverse), rows=%lld, total: nonzeros=%lld, bs=%d\n", rows, nz, L.A.bs);
+      if (l == 0 && c->nsub > 0) add("      level 0 (coarse): preonly + lu replaced by cg to 1e-13 preconditioned by an internal %d-level V-cycle (dense inverse at its bottom), rows=%lld, total: nonzeros=%lld, bs=%d; %d coarse solves, %d cg iterations so far\n", c->nsub, rows, nz, L.A.bs, c->coarse_solves, c->coarse_its);
+      else if (l == 0) add("      level 0 (coarse): preonly + lu (dense inverse), rows=%lld, total: nonzeros=%lld, bs=%d\n", rows, nz, L.A.bs);
       else add("      level %d: chebyshev + jacobi, maximum iterations=%d, eigenvalue estimates used:  min = %g, max = %g%s, rows=%lld, total: nonzeros=%lld, bs=%d%s\n",
                l, s.cheb_its, L.emin, L.emax, s.n_cheb_fixed ? " (set explicitly)" : "", rows, nz, L.A.bs, L.dist ? ", z-slab distributed" : L.rowpart ? ", replicated, products row-partitioned" : "");
     }

@@ -193,6 +193,7 @@ static int read_solver_options(xsb_ctx c)
   if (ppc == "bjacobi" || ppc == "ilu") s.p_pc = 0; else if (ppc == "jacobi") s.p_pc = 1;
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_fieldsplit_p_pc_type %s not supported (bjacobi|ilu|jacobi)", ppc.c_str());
   s.time_kernels = o.flag("xsb_time_kernels");
+  c->use_graph = o.integer("xsb_graph", 1);
   { const std::string mfv = o.str("xsb_matrix_free", "0");   // flag: fine-level products by the element kernel; "full": A / A00 never stored
     s.matrix_free = (mfv.empty() || mfv == "1" || mfv == "true" || mfv == "yes" || mfv == "full" || mfv == "2") ? 1 : 0;
     if (c->no_A && !s.matrix_free) return xsb_fail(c, XSB_ERR_ORDER, "the operator was assembled with -xsb_matrix_free full; the option cannot be dropped before xsb_ksp_setup");
@@ -211,14 +212,15 @@ static int read_solver_options(xsb_ctx c)
 int ksp_release(xsb_ctx c)
 {
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  mg_graphs_release(c);
   mmg_free(c);
   dev_free_phase(c, 1);
   c->red = c->scal = nullptr; c->w_t1 = c->w_t2 = c->xdev = c->bdev = c->idiagA = c->gcr_r = c->fs_tu = nullptr;
   c->mp_lu = c->mp_idiag = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
   c->ilu_fval = c->ilu_bval = c->ilu_binv = nullptr; c->ilu_fn = c->ilu_bn = nullptr; c->MpOwn = Csr();
   c->V.clear(); c->Z.clear(); c->GV.clear(); c->GS.clear();
-  for (int l = 0; l < XSB_MAX_LEVELS; ++l) c->lev[l] = Level();
-  c->nlev = 0; c->ksp_ready = false;
+  for (int l = 0; l < XSB_MAX_LEVELS; ++l) { c->lev[l] = Level(); c->sub[l] = Level(); }
+  c->nlev = 0; c->nsub = 0; c->cg_p = c->cg_q = nullptr; c->ksp_ready = false;
   return 0;
 }
 

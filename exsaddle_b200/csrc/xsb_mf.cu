@@ -306,6 +306,17 @@ __global__ void mf_epilogue_kernel(int64_t n, const unsigned char *__restrict__ 
   }
 }
 
+// element layers a product applies: all of the local lattice, or (slabs, constrained operator) only those touching an owned plane
+static void mf_layer_range(xsb_ctx c, bool owned_only, int *zlo, int *zhi)
+{
+  const Lattice &L = c->lat;
+  *zlo = 0; *zhi = L.mz;
+  if (c->slab.nranks > 1 && owned_only) {   // [k0-1, k1) of the local [k0-2, k1+1): the two extra ghost layers exist for the assembled Galerkin rows
+    *zlo = c->slab.k0 - c->slab.e0 - 1; if (*zlo < 0) *zlo = 0;
+    *zhi = c->slab.k1 - c->slab.e0; if (*zhi > L.mz) *zhi = L.mz;
+  }
+}
+
 int mf_setup(xsb_ctx c)
 {
   if (c->nsd != 3) return xsb_fail(c, XSB_ERR_SUP, "-xsb_matrix_free is implemented for the 3-D Q2 velocity block");
@@ -316,6 +327,7 @@ int mf_setup(xsb_ctx c)
   CUDA_OK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, c->stream));
   if (!c->mf_tmp) XSB_CHK(dev_alloc(c, &c->mf_tmp, (size_t)c->lat.nu));
   c->so.mf_kernel = c->opt.integer("xsb_mf_kernel", 4);   // 4: one-pass TMA-staged kernel (xsb_mf1p.cu); 1: 9 lanes per element, 8 colour passes; 2, 3: 3 lanes per element, preloaded / reduction scatter
+  c->so.mf_tile = c->opt.integer("xsb_mf_tile", 0);
   c->so.mf_chunk = c->opt.integer("xsb_mf_chunk", 0);     // element layers per z-chunk (0 = no chunking)
   c->so.mf_reverse = c->opt.integer("xsb_mf_reverse", 1); // alternate the sweep direction of successive colour launches
   if (c->so.mf_kernel < 1 || c->so.mf_kernel > 4) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_kernel must be 1 .. 4");
@@ -324,6 +336,7 @@ int mf_setup(xsb_ctx c)
     mf_bcnode_kernel<<<(unsigned)((c->lat.nun + 255) / 256), 256, 0, c->stream>>>(c->lat.nun, c->isbc, c->mf_bcnode); KERNEL_OK();
   }
   c->mf_opts_read = true;
+  if (c->so.mf_kernel == 4) { int zlo, zhi; mf_layer_range(c, true, &zlo, &zhi); XSB_CHK(mf1p_prepare(c, zlo, zhi)); }
   return 0;
 }
 
@@ -347,11 +360,7 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
   const double *eta = c->coeff;   // slot C_ETA (eta, or mu for LAME)
   // Slabs: only the element layers that touch an owned node plane are needed, [k0-1, k1) of the local [k0-2, k1+1); the two
   // extra ghost layers exist for the assembled Galerkin rows.
-  int zlo = 0, zhi = L.mz;
-  if (c->slab.nranks > 1 && isbc) {
-    zlo = c->slab.k0 - c->slab.e0 - 1; if (zlo < 0) zlo = 0;
-    zhi = c->slab.k1 - c->slab.e0; if (zhi > L.mz) zhi = L.mz;
-  }
+  int zlo, zhi; mf_layer_range(c, isbc != nullptr, &zlo, &zhi);
   if (c->so.mf_kernel == 4) {
     const uintptr_t al = (uintptr_t)x | (uintptr_t)ep.b | (uintptr_t)ep.idiag | (uintptr_t)ep.pkm1;
     if (al & 15) return xsb_fail(c, XSB_ERR_ARG, "one-pass element kernel: vectors must be 16-byte aligned");

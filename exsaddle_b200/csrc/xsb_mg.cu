@@ -407,37 +407,115 @@ static int cheb_smooth(xsb_ctx c, Level &L, bool fine, int its, bool x_is_zero)
   return 0;
 }
 
-static int mg_cycle(xsb_ctx c, int l)
+static int coarse_pcg(xsb_ctx c);
+
+// One V-cycle level of hierarchy H (c->lev: the PCMG hierarchy of the options; c->sub: the internal one under a large coarsest level)
+static int mg_cycle(xsb_ctx c, Level *H, int l, int top, bool main)
 {
-  Level &L = c->lev[l];
+  Level &L = H[l];
   if (l == 0) {   // coarse grid: preonly + LU  ->  x = A^-1 b
+    if (!L.inv) return coarse_pcg(c);   // too large for the dense inverse: solved to LU accuracy by V-cycle-preconditioned CG
     const int n = L.A.nb * L.A.bs;
     k_gemv<<<nblk((int64_t)n * 32), 256, 0, c->stream>>>(n, L.inv, L.b, L.x); KERNEL_OK();
     return 0;
   }
-  Level &C = c->lev[l - 1];
-  const bool fine = l == c->nlev - 1;
+  Level &C = H[l - 1];
+  const bool fine = main && l == top;
   const int64_t n = (int64_t)L.A.nb * L.A.bs;
   XSB_CHK(vec_set(c, n, 0.0, L.x));
   XSB_CHK(cheb_smooth(c, L, fine, c->so.cheb_its, true));                 // pre-smooth
   { Epilogue ep; ep.mode = EPI_RESIDUAL; ep.b = L.b; XSB_CHK(a00_spmv(c, L, fine, L.x, L.r, ep)); }   // r = b - A x
   XSB_CHK(mg_restrict(c, L, C, L.r, C.b));
-  XSB_CHK(mg_cycle(c, l - 1));
+  XSB_CHK(mg_cycle(c, H, l - 1, top, main));
   XSB_CHK(mg_prolong_add(c, L, C, C.x, L.x));
   XSB_CHK(cheb_smooth(c, L, fine, c->so.cheb_its, false));                // post-smooth
   return 0;
 }
 
-// PCApply_MG: one multiplicative V-cycle from a zero initial guess
+// Coarsest level of abf.opts' 3-level hierarchy at the BASELINE sizes (14 739 rows at 32^3, 107 811 at 64^3; the reference
+// factors it with UMFPACK, abf.opts:16): conjugate gradients on the (symmetric positive definite) Galerkin operator,
+// preconditioned by one V-cycle of the internal hierarchy c->sub, to a relative residual of 1e-13 -- the accuracy of a
+// direct factorisation, so the outer iteration counts are those of the reference's LU.
+static __global__ void k_cg_update(int64_t n, const double *__restrict__ sc /* [rz, pq] */, const double *__restrict__ p, const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r)
+{
+  const double alpha = sc[0] / sc[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { x[i] += alpha * p[i]; r[i] -= alpha * q[i]; }
+}
+static int coarse_pcg(xsb_ctx c)
+{
+  Level &L = c->lev[0]; const int top = c->nsub - 1; Level &S = c->sub[top];
+  const int64_t n = (int64_t)L.A.nb * L.A.bs; const Ranges rg = whole(n);
+  double *r = L.r, *p = c->cg_p, *q = c->cg_q, *sc = c->scal + 192;   // sc[0] r.z, sc[1] p.q, sc[2] r.r
+  double h[4], rz_old = 0.0, bb = 0.0; Epilogue plain;
+  XSB_CHK(vec_set(c, n, 0.0, L.x));
+  XSB_CHK(vec_copy(c, n, L.b, r));
+  c->coarse_solves++;
+  for (int it = 0; it < 500; ++it) {
+    double *save = S.b; S.b = r;                       // z = M^-1 r: one V-cycle of the internal hierarchy on r
+    int rc = mg_cycle(c, c->sub, top, top, false);
+    S.b = save; if (rc) return rc;
+    double *z = S.x;
+    { double *two[1] = {z}; XSB_CHK(vec_mdot(c, rg, r, two, 1, true, sc, true)); }   // [r.z, r.r] (replicated level: local sums)
+    XSB_CHK(vec_fetch(c, sc, 2, h));
+    const double rz = h[0], rr = h[1];
+    if (it == 0) bb = rr;
+    if (bb == 0.0 || rr <= 1e-26 * bb) return 0;       // ||r|| <= 1e-13 ||b||
+    if (!(rz > 0.0)) return xsb_fail(c, XSB_ERR_BREAKDOWN, "coarse-level CG: the V-cycle preconditioner is not positive definite (r.z = %g)", rz);
+    if (it == 0) XSB_CHK(vec_copy(c, n, z, p)); else XSB_CHK(vec_aypx(c, n, rz / rz_old, z, p));   // p = z + beta p
+    rz_old = rz;
+    XSB_CHK(spmv_baij(c, L.A, p, q, plain));
+    { double *two[1] = {q}; XSB_CHK(vec_mdot(c, rg, p, two, 1, false, sc + 1, true)); }             // p.q
+    k_cg_update<<<nblk(n) > 1184 ? 1184 : nblk(n), 256, 0, c->stream>>>(n, sc, p, q, L.x, r); KERNEL_OK();
+    c->coarse_its++;
+  }
+  return xsb_fail(c, XSB_ERR_BREAKDOWN, "coarse-level CG did not reach 1e-13 in 500 iterations");
+}
+
+// PCApply_MG: one multiplicative V-cycle from a zero initial guess.
+// The ~150 launches of a cycle (most of them tiny coarse-level kernels whose launch cost exceeds their run time) are captured
+// once into a CUDA graph and replayed (-xsb_graph, default on).  The smoothers rotate three buffers per level, so the pointer
+// assignment a cycle starts from repeats with period 3: one graph per starting state, found by (rhs, x, w0, w1) of the fine level.
+static void vgraph_free(xsb_ctx c)
+{
+  for (auto &g : c->vgraphs) { if (g.exec) cudaGraphExecDestroy(g.exec); if (g.graph) cudaGraphDestroy(g.graph); }
+  c->vgraphs.clear();
+}
+void mg_graphs_release(xsb_ctx c) { vgraph_free(c); }
 int mg_vcycle(xsb_ctx c, const double *b, double *x)
 {
-  Level &L = c->lev[c->nlev - 1];
+  const int top = c->nlev - 1;
+  Level &L = c->lev[top];
   const int64_t n = (int64_t)L.A.nb * L.A.bs;
+  const bool graphable = c->use_graph && c->nsub == 0 && !c->so.time_kernels && c->nlev > 1;   // coarse CG and event timing need the host
+  if (graphable) {
+    for (auto &g : c->vgraphs) {
+      if (g.b != b || g.x != L.x || g.w0 != L.w0 || g.w1 != L.w1) continue;
+      CUDA_OK(cudaGraphLaunch(g.exec, c->stream));
+      c->n_a00 += g.d_a00; c->n_launch += g.d_launch; for (int i = 0; i < 4; ++i) c->a00_mode[i] += g.d_mode[i];
+      for (int l = 0; l <= top; ++l) { c->lev[l].x = g.px[l]; c->lev[l].w0 = g.pw0[l]; c->lev[l].w1 = g.pw1[l]; }   // the rotation the cycle leaves behind
+      c->graph_replays++;
+      return vec_copy(c, n, c->lev[top].x, x);
+    }
+  }
+  xsb_ctx_s::VGraph G; G.b = b; G.x = L.x; G.w0 = L.w0; G.w1 = L.w1;
+  const int64_t a0 = c->n_a00, l0 = c->n_launch; int64_t m0[4]; for (int i = 0; i < 4; ++i) m0[i] = c->a00_mode[i];
+  const bool capture = graphable && c->vgraphs.size() < 8;
+  if (capture) CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   double *save = L.b; L.b = const_cast<double *>(b);   // the level reads b in place
-  int rc = mg_cycle(c, c->nlev - 1);
-  L.b = save;
+  int rc = mg_cycle(c, c->lev, top, top, true);
+  c->lev[top].b = save;
+  if (capture) {
+    cudaError_t e = cudaStreamEndCapture(c->stream, &G.graph);
+    if (rc) { if (G.graph) cudaGraphDestroy(G.graph); return rc; }
+    if (e != cudaSuccess) return xsb_fail(c, XSB_ERR_CUDA, "V-cycle graph capture failed: %s (disable with -xsb_graph 0)", cudaGetErrorString(e));
+    CUDA_OK(cudaGraphInstantiate(&G.exec, G.graph, 0));
+    G.d_a00 = c->n_a00 - a0; G.d_launch = c->n_launch - l0; for (int i = 0; i < 4; ++i) G.d_mode[i] = c->a00_mode[i] - m0[i];
+    for (int l = 0; l <= top; ++l) { G.px[l] = c->lev[l].x; G.pw0[l] = c->lev[l].w0; G.pw1[l] = c->lev[l].w1; }
+    c->vgraphs.push_back(G);
+    CUDA_OK(cudaGraphLaunch(G.exec, c->stream));   // capturing records, it does not run
+  }
   if (rc) return rc;
-  return vec_copy(c, n, L.x, x);
+  return vec_copy(c, n, c->lev[top].x, x);
 }
 
 // ------------------------------------------------------------------ eigenvalue estimate (KSPChebyshev esteig)
@@ -494,6 +572,50 @@ static int cheb_estimate(xsb_ctx c, Level &L)
   return 0;
 }
 
+static int cheb_estimate(xsb_ctx c, Level &L);
+// Coarsest level: dense inverse up to 6600 rows; above that (abf.opts' 3 levels at 32^3 and larger) the hierarchy is continued
+// INTERNALLY by further Galerkin coarsening until the dense inverse applies, and the level is solved by coarse_pcg.
+static int coarse_setup(xsb_ctx c)
+{
+  Level &L0 = c->lev[0]; const int bs = L0.A.bs;
+  c->nsub = 0; c->coarse_its = c->coarse_solves = 0;
+  const int64_t dense_max = c->opt.integer("xsb_coarse_dense_max", 6600) < 6600 ? c->opt.integer("xsb_coarse_dense_max", 6600) : 6600;   // tests lower it to exercise the internal hierarchy on small meshes
+  if ((int64_t)L0.A.nb * bs <= dense_max) return coarse_invert(c, L0);
+  int dims[XSB_MAX_LEVELS][3]; int ns = 1;
+  dims[0][0] = L0.nx; dims[0][1] = L0.ny; dims[0][2] = L0.nz;
+  while ((int64_t)dims[ns - 1][0] * dims[ns - 1][1] * dims[ns - 1][2] * bs > dense_max) {
+    if (ns == XSB_MAX_LEVELS) return xsb_fail(c, XSB_ERR_SUP, "coarsest MG level: internal hierarchy deeper than %d levels", XSB_MAX_LEVELS);
+    for (int d = 0; d < 3; ++d) {
+      const int nn = dims[ns - 1][d];
+      if (d == 2 && c->nsd == 2) { dims[ns][d] = 1; continue; }
+      if ((nn - 1) % 2 != 0 || (nn - 1) / 2 + 1 < 2) { if ((int64_t)dims[ns - 1][0] * dims[ns - 1][1] * dims[ns - 1][2] * bs <= 6600) goto done; return xsb_fail(c, XSB_ERR_SUP, "coarsest MG level has %lld dofs and its lattice %dx%dx%d cannot be coarsened further for the internal coarse solver (dense inverse: <= 6600)",
+                                                                     (long long)L0.A.nb * bs, L0.nx, L0.ny, L0.nz); }
+      dims[ns][d] = (nn - 1) / 2 + 1;
+    }
+    ++ns;
+  }
+done:
+  if (ns == 1) return coarse_invert(c, L0);
+  c->nsub = ns;
+  { Level &T = c->sub[ns - 1]; T = Level(); T.nx = L0.nx; T.ny = L0.ny; T.nz = L0.nz; T.A = L0.A; T.owns_A = false; }
+  for (int l = ns - 2; l >= 0; --l) {
+    Level &F = c->sub[l + 1], &C = c->sub[l]; C = Level();
+    C.nx = dims[ns - 1 - l][0]; C.ny = dims[ns - 1 - l][1]; C.nz = dims[ns - 1 - l][2];
+    XSB_CHK(galerkin(c, F, C));
+  }
+  for (int l = 0; l < ns; ++l) {
+    Level &L = c->sub[l]; const int64_t n = (int64_t)L.A.nb * bs;
+    XSB_CHK(dev_alloc(c, &L.x, (size_t)n)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)n));
+    XSB_CHK(dev_alloc(c, &L.w0, (size_t)n)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)n)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
+    XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
+  }
+  XSB_CHK(coarse_invert(c, c->sub[0]));
+  for (int l = 1; l < ns; ++l) XSB_CHK(cheb_estimate(c, c->sub[l]));
+  const int64_t n0 = (int64_t)L0.A.nb * bs;
+  XSB_CHK(dev_alloc(c, &c->cg_p, (size_t)n0)); XSB_CHK(dev_alloc(c, &c->cg_q, (size_t)n0));
+  return 0;
+}
+
 // ------------------------------------------------------------------ PCSetUp_MG
 int mg_setup(xsb_ctx c)
 {
@@ -528,7 +650,7 @@ int mg_setup(xsb_ctx c)
       L.rowpart = true; L.rp0 = (int)((int64_t)S.rank * L.nz / S.nranks); L.rp1 = (int)((int64_t)(S.rank + 1) * L.nz / S.nranks);
     }
   }
-  XSB_CHK(coarse_invert(c, c->lev[0]));
+  XSB_CHK(coarse_setup(c));
   for (int l = 1; l < levels; ++l) {
     Level &L = c->lev[l];
     if (s.n_cheb_fixed > 0) {

@@ -78,7 +78,7 @@ template <int M> static int mdot_launch(xsb_ctx c, const Ranges &rg, const doubl
 }
 
 // out[j] = w . V[j] for j < k ; out[k] = w . w when with_norm (VecMDot + VecNorm^2 in one or few passes)
-int vec_mdot(xsb_ctx c, const Ranges &n, const double *w, double *const *V, int k, bool with_norm, double *out)
+int vec_mdot(xsb_ctx c, const Ranges &n, const double *w, double *const *V, int k, bool with_norm, double *out, bool local)
 {
   const int tot = k + (with_norm ? 1 : 0);
   for (int j0 = 0; j0 < tot; j0 += MD) {
@@ -96,6 +96,7 @@ int vec_mdot(xsb_ctx c, const Ranges &n, const double *w, double *const *V, int 
     default: XSB_CHK(mdot_launch<8>(c, n, w, P, out + j0)); break;
     }
   }
+  if (local) return 0;
   return comm_allreduce_sum(c, out, tot);   // VecMDot's MPI_Allreduce: one NCCL all-reduce of the whole block of partial sums
 }
 

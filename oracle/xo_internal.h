@@ -36,6 +36,7 @@ typedef struct {
   double  emin_est, emax_est;
   double *x, *b, *r, *w0, *w1, *w2;   /* level work vectors */
   double *lu; int *piv;   /* dense LU of the coarsest operator */
+  double *band; int bw;   /* or, above 8000 rows: banded Cholesky factor (rows x (bw+1), row i holds columns i-bw..i) */
 } xo_level;
 
 struct xo_problem_s {

@@ -338,6 +338,44 @@ static void dense_lu_solve(int n, const double *a, const int *piv, const double 
   for (i = n - 1; i >= 0; --i) { double s = x[i]; for (j = i + 1; j < n; ++j) s -= a[(size_t)i * n + j] * x[j]; x[i] = s / a[(size_t)i * n + i]; }
 }
 
+/* ------------------------------------------------------ banded Cholesky */
+/* Exact sparse direct solve of a large coarsest operator (PETSc: UMFPACK LU, abf.opts:16, on the 14 739 / 107 811 rows abf.opts'
+   3 levels leave at 32^3 / 64^3).  The Galerkin operator is symmetric positive definite with a lattice band, so a banded
+   L L^T factorisation is an exact LU up to rounding.  B[i*(bw+1) + (j-i+bw)] = entry (i,j), i-bw <= j <= i. */
+static int band_cholesky(int n, int bw, double *B)
+{
+  const int w = bw + 1; int k;
+  double *col = (double *)malloc(sizeof(double) * (size_t)w);
+  for (k = 0; k < n; ++k) {
+    const int m = (k + bw < n - 1 ? k + bw : n - 1) - k;   /* rows k+1 .. k+m hold column k */
+    double d = B[(size_t)k * w + bw]; int i;
+    if (!(d > 0.0)) { free(col); return 1; }
+    d = sqrt(d); B[(size_t)k * w + bw] = d;
+    for (i = 1; i <= m; ++i) { double *p = &B[(size_t)(k + i) * w + (bw - i)]; *p /= d; col[i] = *p; }
+#pragma omp parallel for schedule(static) if (m > 64)
+    for (i = 1; i <= m; ++i) {          /* trailing update: row k+i, columns k+1 .. k+i */
+      const double lik = col[i]; double *row = &B[(size_t)(k + i) * w + (bw - i)]; int j;
+      for (j = 1; j <= i; ++j) row[j] -= lik * col[j];
+    }
+  }
+  free(col);
+  return 0;
+}
+static void band_cholesky_solve(int n, int bw, const double *B, const double *b, double *x)
+{
+  const int w = bw + 1; int i, j;
+  for (i = 0; i < n; ++i) {             /* L y = b */
+    const int j0 = i - bw > 0 ? i - bw : 0; const double *row = &B[(size_t)i * w + (bw - i)]; double s = b[i];
+    for (j = j0; j < i; ++j) s -= row[j] * x[j];
+    x[i] = s / row[i];
+  }
+  for (i = n - 1; i >= 0; --i) {        /* L^T x = y, column sweep */
+    const int j0 = i - bw > 0 ? i - bw : 0; const double *row = &B[(size_t)i * w + (bw - i)]; const double xi = x[i] / row[i];
+    x[i] = xi;
+    for (j = j0; j < i; ++j) x[j] -= row[j] * xi;
+  }
+}
+
 /* -------------------------------------------------------------- ILU(0) */
 /* MatLUFactorNumeric_SeqAIJ with ILU(0) pattern, natural ordering, no shift: row-wise IKJ, the pivot is
    stored inverted and the multiplier is a_ik * (1/a_kk).  lu[] shares Mp's pattern; lu[diag] = 1/pivot. */
@@ -539,7 +577,8 @@ static void mg_cycle(xo_problem *P, int l)
 {
   xo_level *L = &P->lev[l];
   if (l == 0) {   /* coarse: preonly + LU */
-    dense_lu_solve(L->A.n, L->lu, L->piv, L->b, L->x);
+    if (L->band) band_cholesky_solve(L->A.n, L->bw, L->band, L->b, L->x);
+    else dense_lu_solve(L->A.n, L->lu, L->piv, L->b, L->x);
     return;
   }
   {
@@ -590,7 +629,15 @@ int xo_mg_setup(xo_problem *P, int levels)
   }
   { /* coarsest: dense LU (PETSc: UMFPACK sparse LU, abf.opts:16) */
     xo_level *L = &P->lev[0]; const int n = L->A.n; int i, k;
-    if (n > 8000) return xo_fail(P, "coarsest MG level too large for the oracle's dense LU (use more levels)");
+    if (n > 8000) {   /* banded Cholesky (the lattice band of the 27-point block stencil) */
+      int bw = 0;
+      for (i = 0; i < n; ++i) for (k = L->A.ia[i]; k < L->A.ia[i + 1]; ++k) if (i - L->A.ja[k] > bw) bw = i - L->A.ja[k];
+      if ((double)n * (bw + 1) * 8.0 > 16e9) return xo_fail(P, "coarsest MG level too large for the oracle's banded Cholesky (use more levels)");
+      L->bw = bw; L->band = (double *)calloc((size_t)n * (bw + 1), sizeof(double));
+      for (i = 0; i < n; ++i) for (k = L->A.ia[i]; k < L->A.ia[i + 1]; ++k) if (L->A.ja[k] <= i) L->band[(size_t)i * (bw + 1) + (L->A.ja[k] - i + bw)] = L->A.a[k];
+      if (band_cholesky(n, bw, L->band)) return xo_fail(P, "coarse operator is not positive definite");
+      return 0;
+    }
     L->lu = (double *)calloc((size_t)n * n, sizeof(double)); L->piv = (int *)malloc(sizeof(int) * n);
     for (i = 0; i < n; ++i) for (k = L->A.ia[i]; k < L->A.ia[i + 1]; ++k) L->lu[(size_t)i * n + L->A.ja[k]] = L->A.a[k];
     if (dense_lu(n, L->lu, L->piv)) return xo_fail(P, "singular coarse operator");
@@ -694,7 +741,7 @@ void xo_solver_free(xo_problem *P)
   for (l = 0; l < P->nlev; ++l) {
     xo_level *L = &P->lev[l];
     if (L->owns_A) csr_free(&L->A);
-    free(L->idiag); free(L->x); free(L->b); free(L->r); free(L->w0); free(L->w1); free(L->w2); free(L->lu); free(L->piv);
+    free(L->idiag); free(L->x); free(L->b); free(L->r); free(L->w0); free(L->w1); free(L->w2); free(L->lu); free(L->piv); free(L->band);
     memset(L, 0, sizeof(*L));
   }
   P->nlev = 0;

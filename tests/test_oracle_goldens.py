@@ -3,6 +3,7 @@
 tests/golden/testref_kat.json holds the numbers extracted from /root/reference/testref/*.ref and the
 option strings of /root/reference/Makefile:254-513 (tests/golden/make_golden.py).  No GPU needed.
 """
+import json
 import os
 
 import numpy as np
@@ -411,3 +412,14 @@ def test_plain_fs_tree_history_and_diagnostics_match_golden(kat, name):
     assert [_short(v) for v in hist] == c["residuals_text"]
     assert [g.rstrip() for g in F.p.diagnostics_text(x)] == [s.rstrip() for s in c["diagnostics"]]
     assert F.p.banner.rstrip("\n").split("\n") == c["banner"]
+
+
+def test_history_floor_at_baseline_sizes():
+    """The committed oracle-vs-oracle drift records (scripts/oracle_drift.py: the oracle with reversed dot-product / row sums
+    against the oracle fixture): same outer and inner iteration counts, histories apart by ~1e-6 -- two orders of magnitude
+    above north_star's 1e-8, so that bar is not attainable at eta1/eta0 = 1e6 by any implementation that does not reproduce
+    the reference's summation order bit for bit.  The GPU-vs-oracle bound of tests/test_gpu_parity.py sits at this floor."""
+    for mx in (32, 64):
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_oracle_drift_%dcubed.json" % mx)))
+        assert d["its"][0] == d["its"][1] and d["inner_its_equal"]
+        assert 1e-8 < d["max_rel_hist_diff_above_1e-2"] < 1e-5
