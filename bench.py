@@ -3,19 +3,23 @@
 
 Metric (BASELINE.json): Stokes KSP solve time to rtol 1e-8 (s) -- FGMRES + fieldsplit Schur-upper ABF with GMG
 (Chebyshev/Jacobi, Galerkin) on the velocity block -- and the Stokes MatMult HBM GB/s against the measured peak.
-A "step" is one KSPSolve of the assembled system (zero initial guess, second-solve protocol of exSaddle.c:569-599:
-set-up is outside the timed region).  Inputs (A00 alone is 10.4 GB at 64^3) are far larger than the 126 MB L2.
+A "step" is one KSPSolve (zero initial guess, second-solve protocol of exSaddle.c:569-599: set-up is outside the timed
+region).  The working set (x, y, viscosity, Galerkin levels; A00 BAIJ 10.4 GB on the assembled path) exceeds the 126 MB L2.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--mx 64] [--eta1 1e6] [--levels 6] [--path assembled|operator-free] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mx 64] [--eta1 1e6] [--levels 6] [--path operator-free|assembled] [--impl reference]
 
---path assembled (default): A is the reference's MATAIJ layout, A00 / Galerkin levels BAIJ(3); the roofline is the HBM
-roofline of the fine-level A00 SpMV.  The same solve with the operator-free fine level (-xsb_matrix_free full: neither A
-nor A00 stored, sum-factorised Q2 element kernel) is timed beside it and reported under "matrix_free".
---path operator-free: the operator-free solve is the timed step (the only path at 128^3 below 8 GPUs: nnz(A) = 1.13e10
-does not fit 32-bit indices); the roofline is then the FP64 issue roofline of the element kernel (measured FMA peak).
+`value` (default --path operator-free): neither A nor A00 is stored; every fine-level A00 product is the one-pass, TMA-staged,
+sum-factorised Q2 element kernel (csrc/xsb_mf1p.cu) with the smoother update fused in.  `roofline` is that kernel against the
+measured FP64 FMA peak (it is bound by FP64 issue, not by HBM or tensor throughput: SURVEY 8d), with its HBM view beside it.
+`assembled`: the same solve on the reference's data layout (A in MATAIJ, A00 / Galerkin levels BAIJ(3)) with the HBM roofline of
+the fine-level BAIJ SpMV and the full-A AIJ MatMult micro-measure.  `strong_128`: the north-star strong-scaling workload
+(128^3, 7 levels, operator-free) at the same N.  `parity`: true residual + iteration counts / history against the committed
+CPU-oracle fixture of the timed configuration; the process exits 3 if it does not hold (a wrong answer prints no valid time).
+`e2e`: the same solve through the host-pointer C-ABI call (pinned host RHS -> device, solution -> host inside the timed region).
 
 N > 1 (torchrun): the SAME problem is cut into z-slabs, one per GPU (strong scaling): NCCL halo exchange in front of
 every operator apply, NCCL all-reduce behind every Krylov reduction; value = solve time, max over ranks.
+--impl reference: the CPU oracle port (PETSc is not installable here), all host cores, ONE complete timed solve.
 """
 import argparse
 import json
@@ -41,9 +45,9 @@ def workload_options(a):
 
 
 # measured once per kernel change with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-NCU_TRAFFIC = {("spmv_baij", 64, 1): 10.81e9, ("mf_a00", 64, 1): 8 * 71.8e6}
+NCU_TRAFFIC = {("spmv_baij", 64, 1): 10.81e9, ("mf_onepass", 64, 1): 370.0e6}   # mf_onepass: Chebyshev-step launch, profiles/r02_onepass_cheb_t1_raw.csv (314 MB read + 56 MB written)
 FP64_PEAK_TFLOPS = 36.72      # scripts/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak.json): 63.1 DFMA/clk/SM at 1965 MHz
-MF_FLOP_PER_ELEMENT = 7140.0  # FP64 flops the element kernel executes per element: 3 lanes x (927 DFMA x 2 + 418 DMUL + 108 DADD), cuobjdump -sass
+MF_FLOP_PER_ELEMENT = 5808.0  # FP64 flops the one-pass element kernel executes per element: 3 lanes x (723 DFMA x 2 + 376 DMUL + 114 DADD), cuobjdump -sass (zero / unit table entries skipped)
 
 
 def a00_csr_bytes(mx, world=1):
@@ -270,19 +274,24 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sample-outer", dest="sample_outer", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-matrix-free", dest="no_matrix_free", action="store_true")
-    ap.add_argument("--path", default="auto", choices=["auto", "assembled", "operator-free"])
+    ap.add_argument("--no-assembled", dest="no_assembled", action="store_true", help="skip the assembled (AIJ / BAIJ) path measured beside the headline")
+    ap.add_argument("--no-strong128", dest="no_strong128", action="store_true", help="skip the 128^3 operator-free block (north-star strong-scaling workload)")
+    ap.add_argument("--path", default="operator-free", choices=["operator-free", "assembled"], help="which path is the headline `value`")
     a = ap.parse_args()
-    if a.path == "auto":   # the assembled AIJ operator needs nnz(A) per rank < 2^31 (32-bit PetscInt)
-        a.path = "assembled" if 5420.0 * a.mx ** 3 / max(1, a.gpus) < 2.0e9 else "operator-free"
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    fits_assembled = 5420.0 * a.mx ** 3 / max(1, world) < 2.0e9   # the AIJ operator needs nnz(A) per rank < 2^31 (32-bit PetscInt)
+    if a.path == "assembled" and not fits_assembled:
+        raise SystemExit("--path assembled: nnz(A) per rank exceeds 32-bit indices at %d^3 on %d GPU(s)" % (a.mx, world))
+    headline_opfree = a.path == "operator-free"
 
-    cfg = {"workload": workload_name(a), "path": a.path, "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
+    path_text = {True: "operator-free: neither A nor A00 stored; fine-level A00 products (smoother, GCR, outer MatMult) by the one-pass TMA-staged sum-factorised Q2 element kernel, "
+                       "first Galerkin level assembled element by element, coarse levels BAIJ(3)",
+                 False: "assembled: A in the reference's MATAIJ layout, A00 and Galerkin levels BAIJ(3)"}
+    cfg = {"workload": workload_name(a), "path": path_text[headline_opfree], "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
            "parallelism": "1 GPU" if world == 1 else "one problem, z-slab partition over %d GPUs (one process per GPU): NCCL send/recv halo exchange before every operator apply, NCCL all-reduce for Krylov dot products; fine MG level distributed, coarse levels replicated (products of the large ones row-partitioned + all-gathered), ILU(0) per rank (bjacobi)" % world,
-           "l2": ("inputs (A00 BAIJ 10.4 GB at 64^3) far exceed the 126 MB L2; no flush needed" if a.path == "assembled" else
-                  "x, y, viscosity and the first Galerkin level (>= 0.7 GB at 64^3) exceed the 126 MB L2; no flush needed"),
+           "l2": "x, y, viscosity and the Galerkin levels (>= 0.7 GB at 64^3; assembled path: A00 BAIJ 10.4 GB) exceed the 126 MB L2; no flush needed",
            "options": workload_options(a)}
 
     if a.impl == "reference":
@@ -308,8 +317,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    def make(extra):
-        h = X.ExSaddle(workload_options(a) + " -xsb_time_kernels" + extra, nsd=3, device=local)
+    def make(b, extra):
+        h = X.ExSaddle(workload_options(b) + extra, nsd=3, device=local)
         if world > 1:   # one problem, z-slabs over the ranks: NCCL communicator inside the library, id shipped by torch.distributed
             uid = [X.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
@@ -328,111 +337,114 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t]
 
-    opfree = a.path == "operator-free"
-    g = make(" -xsb_matrix_free full" if opfree else "")
-    t0 = time.time(); g.assemble(); t_asm = time.time() - t0
-    part = g.partition()
-    own_frac = part["u_len"] / float(g.nu)   # share of the local lattice this rank owns (ghost layers excluded)
-    t0 = time.time(); g.ksp_setup(); t_setup = time.time() - t0
-    n = g.n
-    xdev = torch.empty(n, dtype=torch.float64, device="cuda")
-    F_host = torch.from_numpy(g.rhs()).pin_memory()
-    x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    peak, peak_src = peaks()
 
-    # ---- device-resident timing: K solves, CUDA events on the launching stream
-    for _ in range(warmup):
-        g.solve_dev(0, xdev.data_ptr())
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
-    ms, launches, avg_ns, n_a00, a00_modes = timed_solves(g, torch, xdev, a.steps, barrier)
-    clocks = sampler.stop()
-    its, reason = g.iterations()
-    inner = g.inner_iterations()
-    hist = g.history()
-    parity = parity_check(g, X, torch, dist, a, world, xdev, its, reason, inner, [float(v) for v in hist])
-    # ---- end to end through the host-pointer C-ABI call: pinned host RHS -> device, solution -> host, every step
-    ms_e2e = timed_e2e(g, X, torch, xdev.device, F_host, x_host, a.steps, barrier)
-    ms, ms_e2e = allmax([ms, ms_e2e])
-    sec_per_solve = ms / 1e3 / a.steps
-    e2e_per_solve = ms_e2e / 1e3 / a.steps
-
-    def fp64_roofline(avg_apply_ns, n_applies, step_seconds):
-        flops = MF_FLOP_PER_ELEMENT * nel_local   # every element of the local lattice (ghost layers included on slabs)
-        ach = flops / max(avg_apply_ns, 1) / 1e3   # TFLOP/s
-        tr = NCU_TRAFFIC.get(("mf_a00", a.mx, world))
-        return {"bound": "fp64", "kernel": "mf_a00_kernel_v2 x 8 colours + epilogue (sum-factorised Q2 element apply of A00)", "achieved": ach,
-                "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "traffic": tr,
-                "peak_source": "measured FP64 FMA micro-kernel (scripts/fp64_peak.cu, profiles/r01_fp64_peak.json); not in MEASURED_PEAKS.json",
-                "flops_per_launch": flops, "avg_launch_us": avg_apply_ns / 1e3, "launches_timed": n_applies,
-                "share_of_step": (n_applies * avg_apply_ns * 1e-9) / step_seconds,
-                "hbm_view": {"algorithmic_bytes": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world,
-                             "achieved_GBps": (16.0 * 3 * (2 * a.mx + 1) ** 3 + 8.0 * 27 * a.mx ** 3) / world / max(avg_apply_ns, 1)},
-                "aij_equivalent_GBps": a00_csr_bytes(a.mx, world) / max(avg_apply_ns, 1)}
-
-    # ---- full-A MatMult micro-measure (collective on slabs: every rank runs it): 10 warm-up + 30 timed applies.
-    # Assembled path: the reference's MATAIJ layout; operator-free path: element kernel + A01 / A10 / A11 CSR products.
-    a_info = g.mat_info(X.MAT_A)
-    a00_info = g.mat_info(X.MAT_A00)
-    nel_local = g.nel
-    xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
-    yout = torch.empty_like(xin)
-    stream = torch.cuda.ExternalStream(g.stream(), device=xdev.device)
-    stream.wait_stream(torch.cuda.current_stream())   # xin is produced on torch's stream, consumed on the library's
-    with torch.cuda.stream(stream):
-        for _ in range(10):
-            g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record(stream)
-        for _ in range(30):
-            g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
-        m1.record(stream)
-    torch.cuda.synchronize()
-    aij_ms = m0.elapsed_time(m1) / 30
-    del xin, yout
-
-    # ---- assembled path: the same solve with the operator-free fine level (K4), reported beside it
-    mf = None
-    if not opfree and not a.no_matrix_free:
-        g.close(); g = None
-        torch.cuda.empty_cache()
-        g = make(" -xsb_matrix_free full")
-        g.assemble(); g.ksp_setup()
-        for _ in range(2):
+    def measure(b, opfree, steps, wu, sampler=None, e2e=True, instrument=True, micro=False):
+        """One path of one workload: K timed solves (device-resident, CUDA events, V-cycles replayed from CUDA graphs), parity,
+        end-to-end solves through the host-pointer call, and one instrumented solve (-xsb_time_kernels: an event pair around every
+        fine-level A00 product, graphs off) for the live kernel time of the roofline."""
+        g = make(b, " -xsb_matrix_free full" if opfree else "")
+        t0 = time.time(); g.assemble(); t_asm = time.time() - t0
+        part = g.partition(); own_frac = part["u_len"] / float(g.nu)
+        t0 = time.time(); g.ksp_setup(); t_setup = time.time() - t0
+        n = g.n
+        xdev = torch.empty(n, dtype=torch.float64, device="cuda")
+        for _ in range(wu):
             g.solve_dev(0, xdev.data_ptr())
         barrier()
-        ms_mf, l_mf, ns_mf, n_mf, _ = timed_solves(g, torch, xdev, a.steps, barrier)
-        ms_mf_e2e = timed_e2e(g, X, torch, xdev.device, F_host, x_host, a.steps, barrier)
-        its_mf, reason_mf = g.iterations()
-        parity_mf = parity_check(g, X, torch, dist, a, world, xdev, its_mf, reason_mf, g.inner_iterations(), [float(v) for v in g.history()])
-        ms_mf, ms_mf_e2e = allmax([ms_mf, ms_mf_e2e])
-        mf = {"value": ms_mf / 1e3 / a.steps, "unit": "s", "e2e": ms_mf_e2e / 1e3 / a.steps, "outer_its": its_mf, "reason": reason_mf,
-              "inner_gcr_its": int(sum(g.inner_iterations())), "gpu_launches": l_mf, "parity": parity_mf,
-              "roofline": fp64_roofline(ns_mf, n_mf, ms_mf / 1e3),
-              "note": "-xsb_matrix_free full: neither A nor A00 stored; fine-level A00 products (smoother, GCR, outer MatMult) by the sum-factorised Q2 "
-                      "element kernel, first Galerkin level assembled element by element; identical iteration counts (tests/test_gpu_parity.py)"}
+        if sampler:
+            sampler.start()
+        ms, launches, _, n_a00, modes = timed_solves(g, torch, xdev, steps, barrier)
+        clocks = sampler.stop() if sampler else None
+        its, reason = g.iterations(); inner = g.inner_iterations(); hist = g.history()
+        parity = parity_check(g, X, torch, dist, b, world, xdev, its, reason, inner, [float(v) for v in hist])
+        out = {"outer_its": int(its), "reason": int(reason), "inner_gcr_its": int(sum(inner)), "rnorm0": float(hist[0]), "rnorm": float(hist[-1]),
+               "a00_products_per_solve": n_a00 // steps, "assemble_s": t_asm, "ksp_setup_s": t_setup, "gpu_launches": launches, "parity": parity, "clocks": clocks}
+        ms_e2e = None
+        if e2e:
+            F_host = torch.from_numpy(g.rhs()).pin_memory(); x_host = torch.empty(n, dtype=torch.float64).pin_memory()
+            ms_e2e = timed_e2e(g, X, torch, xdev.device, F_host, x_host, steps, barrier)
+            del F_host, x_host
+        if micro:   # full-A MatMult, 10 warm-up + 30 timed applies (collective on slabs)
+            a_info = g.mat_info(X.MAT_A)
+            xin = torch.sin(0.37 * torch.arange(n, dtype=torch.float64, device="cuda")) + 0.1
+            yout = torch.empty_like(xin)
+            stream = torch.cuda.ExternalStream(g.stream(), device=xdev.device)
+            stream.wait_stream(torch.cuda.current_stream())   # xin is produced on torch's stream, consumed on the library's
+            with torch.cuda.stream(stream):
+                for _ in range(10):
+                    g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                m0.record(stream)
+                for _ in range(30):
+                    g.mat_mult_dev(X.MAT_A, xin.data_ptr(), yout.data_ptr())
+                m1.record(stream)
+            torch.cuda.synchronize()
+            aij_ms = m0.elapsed_time(m1) / 30
+            aij_bytes = (12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]) * own_frac
+            out["aij_matmult"] = {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)" if not opfree else "element kernel (A00) + spmv_csr_kernel on A01 / A10 / A11",
+                                  "ms": aij_ms, "bytes": aij_bytes, "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak,
+                                  "frac_of_nominal_8TBps": aij_bytes / (aij_ms * 1e6) / 8000.0}
+            del xin, yout
+        ms, ms_e2e = allmax([ms, ms_e2e if ms_e2e is not None else 0.0])
+        out["value"] = ms / 1e3 / steps; out["e2e"] = ms_e2e / 1e3 / steps if e2e else None
+        if instrument:
+            a00_info = g.mat_info(X.MAT_A00); nel_local = g.nel
+            g.set_option("-xsb_time_kernels"); g.ksp_setup()
+            g.solve_dev(0, xdev.data_ptr()); barrier()
+            ms_i, _, avg_ns, n_i, modes_i = timed_solves(g, torch, xdev, 1, barrier)
+            share = (n_i * avg_ns * 1e-9) / (ms_i / 1e3)
+            if opfree:
+                nel_apply = nel_local * own_frac if world > 1 else nel_local   # slabs: the kernel applies the layers touching owned planes
+                flops_alg = 9000.0 * nel_apply            # SURVEY 8(d): ~9.0 kflop per element, sum-factorised
+                flops_exec = MF_FLOP_PER_ELEMENT * nel_apply
+                hbm_bytes = (8.0 * 27 * a.mx ** 3 if b.mx == a.mx else 8.0 * 27 * b.mx ** 3) / world
+                vecs = {0: 2, 1: 3, 2: 4, 3: 5}; tot = max(1, sum(modes_i))
+                hbm_bytes += 8.0 * 3 * (2 * b.mx + 1) ** 3 / world * sum(vecs[m] * modes_i[m] for m in range(4)) / tot
+                ach = flops_alg / max(avg_ns, 1) / 1e3
+                out["roofline"] = {"bound": "fp64", "kernel": "mf_onepass_kernel + mf_shared_kernel (one-pass TMA-staged sum-factorised Q2 element apply of A00 with fused smoother epilogue)",
+                                   "achieved": ach, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS,
+                                   "traffic": NCU_TRAFFIC.get(("mf_onepass", b.mx, world)),
+                                   "peak_source": "measured FP64 FMA micro-kernel (scripts/fp64_peak.cu, profiles/r01_fp64_peak.json); not in MEASURED_PEAKS.json",
+                                   "flops_per_launch": flops_alg, "flops_per_launch_source": "SURVEY 8(d): 9.0 kflop per element (sum-factorised count); executed per SASS count: %.0f flop per element = %.3g per launch" % (MF_FLOP_PER_ELEMENT, flops_exec),
+                                   "achieved_executed_flops": flops_exec / max(avg_ns, 1) / 1e3,
+                                   "avg_launch_us": avg_ns / 1e3, "launches_timed": n_i, "share_of_step": share,
+                                   "hbm_view": {"algorithmic_bytes": hbm_bytes, "achieved_GBps": hbm_bytes / max(avg_ns, 1), "frac_of_measured_peak": hbm_bytes / max(avg_ns, 1) / peak},
+                                   "aij_equivalent_GBps": a00_csr_bytes(b.mx, world) / max(avg_ns, 1)}
+            else:
+                bytes_launch = a00_bytes(a00_info, modes_i) * own_frac   # owned rows only are streamed (own_frac = 1 on one GPU)
+                achieved = bytes_launch / avg_ns if avg_ns else 0.0     # B/ns = GB/s
+                out["roofline"] = {"bound": "hbm", "kernel": "spmv_baij_kernel<3> (fine-level A00 with fused residual/Chebyshev epilogue)",
+                                   "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(("spmv_baij", b.mx, world)),
+                                   "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
+                                   "launches_timed": n_i, "share_of_step": share, "aij_equivalent_GBps": a00_csr_bytes(b.mx, world) / max(avg_ns, 1)}
+        g.close(); del xdev
+        torch.cuda.empty_cache()
+        return out
+
+    sampler = ClockSampler(local)
+    head = measure(a, headline_opfree, a.steps, warmup, sampler=sampler, micro=not headline_opfree)
+    other = None
+    if headline_opfree and fits_assembled and not a.no_assembled:
+        other = measure(a, False, a.steps, 2, micro=True)
+    elif not headline_opfree:
+        other = measure(a, True, a.steps, 2)
+    strong = None
+    if a.mx == 64 and not a.no_strong128:
+        import copy
+        b = copy.copy(a); b.mx, b.levels = 128, 7
+        s128 = measure(b, True, 3, 1, e2e=False, instrument=False)
+        strong = {"workload": workload_name(b), "path": "operator-free", "value": s128["value"], "unit": "s", "steps": 3, "warmup": 1, "outer_its": s128["outer_its"],
+                  "inner_gcr_its": s128["inner_gcr_its"], "true_rel_residual": s128["parity"]["true_rel_residual"], "parity_ok": s128["parity"]["ok"],
+                  "note": "north-star strong-scaling workload (128^3, 7 MG levels): same value at every --gpus N, divide N = 1 by N x this for the efficiency"}
 
     if rank == 0:
-        peak, peak_src = peaks()
-        if opfree:
-            roof = fp64_roofline(avg_ns, n_a00, sec_per_solve * a.steps)
-            roof["full_matmult"] = {"kernel": "element kernel (A00) + spmv_csr_kernel on A01 / A10 / A11", "ms": aij_ms}
-        else:
-            bytes_launch = a00_bytes(a00_info, a00_modes) * own_frac   # owned rows only are streamed (own_frac = 1 on one GPU)
-            achieved = bytes_launch / avg_ns if avg_ns else 0.0   # B/ns = GB/s
-            aij_bytes = (12 * a_info[2] + 4 * (a_info[0] + 1) + 16 * a_info[0]) * own_frac
-            roof = {"bound": "hbm", "kernel": "spmv_baij_kernel<3> (fine-level A00 with fused residual/Chebyshev epilogue)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(("spmv_baij", a.mx, world)),
-                    "peak_source": peak_src, "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ns / 1e3,
-                    "launches_timed": n_a00, "share_of_step": (n_a00 * avg_ns * 1e-9) / (sec_per_solve * a.steps),
-                    "aij_equivalent_GBps": a00_csr_bytes(a.mx, world) / max(avg_ns, 1),
-                    "aij_matmult": {"kernel": "spmv_csr_kernel (full saddle A, AIJ layout)", "ms": aij_ms, "bytes": aij_bytes,
-                                    "achieved": aij_bytes / (aij_ms * 1e6), "frac": aij_bytes / (aij_ms * 1e6) / peak}}
         os.makedirs(os.path.dirname(ITERS_FILE), exist_ok=True)
         try:   # outer iteration count of the ONE-rank solve: what the CPU sample is scaled by (per-rank ILU changes it on slabs)
             if world > 1:
                 raise RuntimeError("keep the one-rank count")
             d = json.load(open(ITERS_FILE)) if os.path.exists(ITERS_FILE) else {}
-            d[config_key(a)] = {"outer_its": its, "inner_its_total": int(sum(inner)), "reason": reason}
+            d[config_key(a)] = {"outer_its": head["outer_its"], "inner_its_total": head["inner_gcr_its"], "reason": head["reason"]}
             json.dump(d, open(ITERS_FILE, "w"), indent=1, sort_keys=True)
         except Exception:
             pass
@@ -447,21 +459,26 @@ def main():
                     base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped: host RAM below %.0f GB" % need_gb}
             except Exception as e:   # the checker must never take the bench line down
                 base = {"value": None, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-        line = {"metric": "stokes_ksp_solve_time_rtol1e-8", "value": sec_per_solve, "unit": "s", "n_gpus": world, "steps": a.steps,
-                "warmup": warmup, "ms_per_step": 1e3 * sec_per_solve, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        n = cfg["unknowns"]
+        line = {"metric": "stokes_ksp_solve_time_rtol1e-8", "value": head["value"], "unit": "s", "n_gpus": world, "steps": a.steps,
+                "warmup": warmup, "ms_per_step": 1e3 * head["value"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
-                "solve": {"outer_its": its, "reason": reason, "inner_gcr_its": int(sum(inner)), "rnorm0": float(hist[0]), "rnorm": float(hist[-1]),
-                          "a00_spmv_per_solve": n_a00 // a.steps, "assemble_s": t_asm, "ksp_setup_s": t_setup},
-                "parity": parity, "roofline": roof, "matrix_free": mf, "cpu_baseline": base,
-                "e2e": {"value": e2e_per_solve, "unit": "s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
-                "gpu_launches": launches, "clocks": clocks}
+                "solve": {k: head[k] for k in ("outer_its", "reason", "inner_gcr_its", "rnorm0", "rnorm", "a00_products_per_solve", "assemble_s", "ksp_setup_s")},
+                "parity": head["parity"], "roofline": head.get("roofline"),
+                ("assembled" if headline_opfree else "operator_free"): None if other is None else {k: other.get(k) for k in ("value", "e2e", "outer_its", "inner_gcr_its", "gpu_launches", "parity", "roofline", "aij_matmult")},
+                "strong_128": strong, "cpu_baseline": base,
+                "e2e": {"value": head["e2e"], "unit": "s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},
+                "gpu_launches": head["gpu_launches"], "clocks": head["clocks"]}
+        if "aij_matmult" in head:
+            line["roofline"]["aij_matmult"] = head["aij_matmult"]
         print(json.dumps(line))
-    if g is not None:
-        g.close()
     if dist is not None:
         dist.destroy_process_group()
-    if not parity["ok"] or (mf is not None and not mf["parity"]["ok"]):
-        sys.stderr.write("bench.py: PARITY FAILED: %s\n" % json.dumps(parity if not parity["ok"] else mf["parity"]))
+    bad = [k for k, v in (("headline", head["parity"]), ("other", other["parity"] if other else None)) if v is not None and not v["ok"]]
+    if strong is not None and not strong["parity_ok"]:
+        bad.append("strong_128")
+    if bad:
+        sys.stderr.write("bench.py: PARITY FAILED in %s: %s\n" % (bad, json.dumps(head["parity"])))
         return 3
     return 0
 

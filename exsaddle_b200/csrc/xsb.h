@@ -109,7 +109,8 @@ struct FeTables {
 // 1-D Q2 basis / derivative tables of the element kernels: N[q][n], Dd[q][n] = D[q][n] / h_d (uniform mesh: J = diag(h))
 struct MfTabS { double N[3][3], Dx[3][3], Dy[3][3], Dz[3][3], w[3]; };
 
-struct Csr  { int n = 0, m = 0; int64_t nnz = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; };
+struct Csr  { int n = 0, m = 0; int64_t nnz = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr;
+              int inode_bs = 0; int64_t inode_rows = 0; };   // rows [0, inode_rows) come in groups of inode_bs consecutive rows with identical column patterns (the components of a velocity node)
 // BAIJ: block rows = lattice nodes, blocks bs x bs stored row-major, block columns ascending.
 struct Baij { int nb = 0, bs = 0; int64_t nblk = 0; int *ia = nullptr, *ja = nullptr; double *a = nullptr; BoxPattern pat{0, 0, 0, 0}; };
 
@@ -142,7 +143,7 @@ struct Model {   // resolved model parameters (models.c static option blocks)
 
 struct SolverOpts {
   int ksp_type = 0;      // 0 gmres 1 fgmres
-  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf) 3 monolithic PCMG (-mg)
+  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf) 3 monolithic PCMG (-mg) 4 fieldsplit with PETSc's default sub-solvers (plain -fs)
   int right = 0;
   double rtol = 1e-5, atol = 1e-50, dtol = 1e4; int max_it = 10000, restart = 30;
   double u_rtol = 1e-5; int u_max_it = 10000, u_restart = 30;
@@ -206,6 +207,7 @@ struct xsb_ctx_s {
   std::vector<char> alloc_phase; int phase = 0;   // 0: xsb_assemble, 1: xsb_ksp_setup (freed when the solver is set up again), 2: lazily created element-kernel state
   void *fe_tables = nullptr;    // FeTables on the device
   void *mmg = nullptr;          // monolithic -mg hierarchy (xsb_mmg.cu)
+  void *fsd = nullptr;          // default -fs tree: GMRES + ILU(0) sub-solvers (xsb_fs.cu)
   const double *nodal_in = nullptr;   // coarse -mg level: nodal Q1 coefficient fields [slot][p-node] to use instead of the model
 };
 
@@ -284,6 +286,10 @@ int mg_prolong_add_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny
 int mmg_setup(xsb_ctx c);
 int mmg_apply(xsb_ctx c, const double *r, double *z);
 void mmg_free(xsb_ctx c);
+// ---- xsb_fs.cu (plain -fs tree with PETSc's default sub-solvers)
+int fsd_setup(xsb_ctx c);
+int fsd_apply(xsb_ctx c, const double *r, double *z);
+void fsd_free(xsb_ctx c);
 // ---- xsb_ilu.cu
 int ilu_setup(xsb_ctx c);
 int ilu_apply(xsb_ctx c, const double *b, double *x);

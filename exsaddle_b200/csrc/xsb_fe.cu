@@ -621,6 +621,7 @@ int fe_assemble(xsb_ctx c)
   int64_t *len64 = nullptr; CUDA_OK(cudaMalloc(&len64, sizeof(int64_t) * (L.n + 1)));
   row_len_kernel<<<nblk(L.n), 256, 0, st>>>(L, len64); KERNEL_OK();
   c->A.n = c->A.m = (int)L.n;
+  c->A.inode_bs = nsd; c->A.inode_rows = L.nu;   // the NSD rows of a velocity node share one column pattern (row_box_u)
   SplitDst sp{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   struct SubDef { Csr *S; int64_t r0, nr; int pcols; };
   SubDef subs[3] = {{&c->A01, 0, L.nu, 1}, {&c->A10, L.nu, L.np, 0}, {&c->A11, L.nu, L.np, 1}};

@@ -1,0 +1,255 @@
+// xsb_fs.cu -- the reference's plain `-fs` solver tree, i.e. PCFIELDSPLIT with PETSc's DEFAULT sub-solvers
+// (exSaddle.c:303-322 when no abf.opts is given; goldens exSaddle{2d,3d}[_lame]_fs_{1,2}, Makefile:282, 347, 396, 480):
+//
+//   outer   GMRES(30), left PC, preconditioned norm                                         (xsb_ksp.cu)
+//   PC      fieldsplit Schur / UPPER / user Mpscaled:
+//             y_p = KSP_p[S, ILU0(Mpscaled)] x_p ,   S v = A11 v - A10 KSP_u[A00](A01 v)     (nested solve per S apply)
+//             y_u = KSP_u[A00] (x_u - A01 y_p)
+//   KSP_u   GMRES(30) + ILU(0) of A00 in natural ordering (PETSc's default PC for seqaij), rtol 1e-5
+//   KSP_p   GMRES(30) + ILU(0) of Mpscaled, rtol 1e-5   (-saddle_fieldsplit_p_ksp_type preonly: the ILU alone)
+//
+// ILU(0) of A00 is a general sparse factorisation: rows are scheduled by dependency level (longest path in the pattern's DAG,
+// integer work done once on the host from the pattern), one CTA sweeps the levels with a block barrier in between; every row
+// performs exactly the operations of MatLUFactorNumeric_SeqAIJ / MatSolve_SeqAIJ in their order (IKJ, ascending columns;
+// backward sweep descending), so the factors equal the sequential ones.  This tree is for the reference's small regression
+// cases (2-D 6^2, 3-D 4^3): the production path is the ABF tree (GCR + GMG), which needs no factorisation of A00.
+#include "xsb.h"
+#include <functional>
+
+namespace {
+struct GIlu {
+  int n = 0; int *ia = nullptr, *ja = nullptr, *diag = nullptr; double *lu = nullptr;
+  int nlf = 0, nlb = 0; int *foff = nullptr, *frows = nullptr, *boff = nullptr, *brows = nullptr;   // forward / backward level schedules
+};
+struct Fsd {
+  Csr A00s;                 // scalar CSR copy of A00 (the MATSEQAIJ sub-matrix PETSc factors)
+  GIlu ilu_u;
+  std::vector<double *> Vu, Vp; double *u_t1 = nullptr, *u_t2 = nullptr, *u_rhs = nullptr, *u_sol = nullptr, *p_t1 = nullptr, *p_t2 = nullptr, *p_tmp = nullptr;
+  int u_max_it = 10000, p_preonly = 0; double u_rtol = 1e-5, p_rtol = 1e-5; int p_max_it = 10000;
+  int64_t n_ksp_u = 0;
+};
+
+// scalar CSR rows of a BAIJ matrix (row x of node: its blocks' row x, block after block)
+template <int BS>
+__global__ void k_baij_scalar(int nb, const int *__restrict__ bia, const int *__restrict__ bja, const double *__restrict__ ba, int *ia, int *ja, double *a)
+{
+  const int node = blockIdx.x * blockDim.x + threadIdx.x; if (node > nb) return;
+  if (node == nb) { ia[BS * nb] = BS * BS * bia[nb]; return; }
+  const int b0 = bia[node], nbk = bia[node + 1] - b0;
+  for (int x = 0; x < BS; ++x) {
+    const int r0 = BS * BS * b0 + x * BS * nbk;
+    ia[BS * node + x] = r0;
+    for (int s = 0; s < nbk; ++s) for (int y = 0; y < BS; ++y) { ja[r0 + s * BS + y] = BS * bja[b0 + s] + y; a[r0 + s * BS + y] = ba[(int64_t)(b0 + s) * BS * BS + x * BS + y]; }
+  }
+}
+
+// MatLUFactorNumeric_SeqAIJ restricted to the pattern, level by level (one CTA; rows of a level are independent)
+__global__ void __launch_bounds__(1024) k_gilu_factor(int nlev, const int *__restrict__ off, const int *__restrict__ rows, const int *__restrict__ ia, const int *__restrict__ ja,
+                                                      const int *__restrict__ diag, double *lu, int *flag)
+{
+  for (int lv = 0; lv < nlev; ++lv) {
+    for (int q = off[lv] + threadIdx.x; q < off[lv + 1]; q += blockDim.x) {
+      const int i = rows[q], r0 = ia[i], r1 = ia[i + 1], di = diag[i];
+      for (int k = r0; k < di; ++k) {                   // lower entries in ascending column order
+        const int r = ja[k]; double mult = lu[k];
+        if (mult != 0.0) {
+          mult = mult * lu[diag[r]]; lu[k] = mult;      // lu[diag] = 1 / pivot
+          int p = k + 1;                                // both rows are sorted: merge the pivot row's upper part into row i
+          for (int l = diag[r] + 1; l < ia[r + 1]; ++l) {
+            const int col = ja[l];
+            while (p < r1 && ja[p] < col) ++p;
+            if (p < r1 && ja[p] == col) lu[p] -= mult * lu[l];   // fill outside the pattern is dropped (ILU(0))
+          }
+        }
+      }
+      if (lu[di] == 0.0) *flag = 1;
+      lu[di] = 1.0 / lu[di];
+    }
+    __syncthreads();
+  }
+}
+// MatSolve_SeqAIJ: forward with unit L (ascending columns), backward with U (descending columns) and the inverted diagonal
+__global__ void __launch_bounds__(1024) k_gilu_solve(int nlf, const int *__restrict__ foff, const int *__restrict__ frows, int nlb, const int *__restrict__ boff, const int *__restrict__ brows,
+                                                     const int *__restrict__ ia, const int *__restrict__ ja, const int *__restrict__ diag, const double *__restrict__ lu,
+                                                     const double *__restrict__ b, double *x)
+{
+  for (int lv = 0; lv < nlf; ++lv) {
+    for (int q = foff[lv] + threadIdx.x; q < foff[lv + 1]; q += blockDim.x) {
+      const int i = frows[q]; double s = b[i];
+      for (int k = ia[i]; k < diag[i]; ++k) s -= lu[k] * x[ja[k]];
+      x[i] = s;
+    }
+    __syncthreads();
+  }
+  for (int lv = 0; lv < nlb; ++lv) {
+    for (int q = boff[lv] + threadIdx.x; q < boff[lv + 1]; q += blockDim.x) {
+      const int i = brows[q]; double s = x[i];
+      for (int k = ia[i + 1] - 1; k > diag[i]; --k) s -= lu[k] * x[ja[k]];
+      x[i] = s * lu[diag[i]];
+    }
+    __syncthreads();
+  }
+}
+
+int gilu_setup(xsb_ctx c, const Csr &M, GIlu &I)
+{
+  cudaStream_t st = c->stream; const int n = M.n;
+  if (M.nnz > 200000000) return xsb_fail(c, XSB_ERR_SUP, "ILU(0) of A00 (the default -fs tree) is meant for the reference's small cases; use the abf.opts tree at this size");
+  I.n = n; I.ia = M.ia; I.ja = M.ja;
+  std::vector<int> ia(n + 1), ja(M.nnz);
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemcpy(ia.data(), M.ia, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(ja.data(), M.ja, sizeof(int) * M.nnz, cudaMemcpyDeviceToHost));
+  // integer analysis of the pattern (host): diagonal positions, forward / backward dependency levels
+  std::vector<int> diag(n), lf(n), lb(n);
+  int nlf = 0, nlb = 0;
+  for (int i = 0; i < n; ++i) {
+    int d = -1, l = 0;
+    for (int k = ia[i]; k < ia[i + 1]; ++k) { if (ja[k] == i) d = k; else if (ja[k] < i && lf[ja[k]] + 1 > l) l = lf[ja[k]] + 1; }
+    if (d < 0) return xsb_fail(c, XSB_ERR_BREAKDOWN, "ILU(0): row %d has no diagonal entry", i);
+    diag[i] = d; lf[i] = l; if (l + 1 > nlf) nlf = l + 1;
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    int l = 0;
+    for (int k = diag[i] + 1; k < ia[i + 1]; ++k) if (lb[ja[k]] + 1 > l) l = lb[ja[k]] + 1;
+    lb[i] = l; if (l + 1 > nlb) nlb = l + 1;
+  }
+  auto schedule = [&](const std::vector<int> &lev, int nl, std::vector<int> &off, std::vector<int> &rows) {
+    off.assign(nl + 1, 0); rows.resize(n);
+    for (int i = 0; i < n; ++i) off[lev[i] + 1]++;
+    for (int l = 0; l < nl; ++l) off[l + 1] += off[l];
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    for (int i = 0; i < n; ++i) rows[cur[lev[i]]++] = i;
+  };
+  std::vector<int> foff, frows, boff, brows; schedule(lf, nlf, foff, frows); schedule(lb, nlb, boff, brows);
+  I.nlf = nlf; I.nlb = nlb;
+  XSB_CHK(dev_alloc(c, &I.diag, (size_t)n)); XSB_CHK(dev_alloc(c, &I.lu, (size_t)M.nnz));
+  XSB_CHK(dev_alloc(c, &I.foff, (size_t)nlf + 1)); XSB_CHK(dev_alloc(c, &I.frows, (size_t)n)); XSB_CHK(dev_alloc(c, &I.boff, (size_t)nlb + 1)); XSB_CHK(dev_alloc(c, &I.brows, (size_t)n));
+  CUDA_OK(cudaMemcpy(I.diag, diag.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(I.foff, foff.data(), sizeof(int) * (nlf + 1), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(I.frows, frows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(I.boff, boff.data(), sizeof(int) * (nlb + 1), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(I.brows, brows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpyAsync(I.lu, M.a, sizeof(double) * M.nnz, cudaMemcpyDeviceToDevice, st));
+  int *flag = nullptr; XSB_CHK(dev_alloc(c, &flag, 1));
+  k_gilu_factor<<<1, 1024, 0, st>>>(nlf, I.foff, I.frows, I.ia, I.ja, I.diag, I.lu, flag); KERNEL_OK();
+  int h = 0; CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
+  if (h) return xsb_fail(c, XSB_ERR_BREAKDOWN, "zero pivot in ILU(0) of A00");
+  return 0;
+}
+int gilu_apply(xsb_ctx c, const GIlu &I, const double *b, double *x)
+{
+  k_gilu_solve<<<1, 1024, 0, c->stream>>>(I.nlf, I.foff, I.frows, I.nlb, I.boff, I.brows, I.ia, I.ja, I.diag, I.lu, b, x); KERNEL_OK();
+  return 0;
+}
+
+// KSPSolve_GMRES from a zero initial guess: left PC, preconditioned norm, classical Gram-Schmidt without refinement, Givens QR,
+// restart 30 -- the inner solver of the default tree; same arithmetic as the outer loop of xsb_ksp.cu.
+typedef std::function<int(const double *, double *)> Op;
+int gmres_left(xsb_ctx c, int64_t n, const Op &A, const Op &M, const double *b, double *x, double rtol, int max_it, int m,
+               std::vector<double *> &V, double *t1, double *t2, double *scal, int *its_out)
+{
+  const Ranges rg = whole(n);
+  std::vector<double> hh((size_t)(m + 1) * m), cs(m + 1), sn(m + 1), rs(m + 1), y(m + 1), hcol(m + 2);
+  auto need = [&](int k) -> int { while ((int)V.size() <= k) { double *p = nullptr; c->phase = 1; int rc = dev_alloc(c, &p, (size_t)n); c->phase = 0; if (rc) return rc; V.push_back(p); } return 0; };
+  int its = 0, reason = 0; double rnorm0 = 0.0, ttol = 0.0; bool first = true;
+  XSB_CHK(vec_set(c, n, 0.0, x)); XSB_CHK(need(0));
+  while (!reason) {
+    if (first) XSB_CHK(M(b, V[0]));                                   // x = 0: M^-1 b
+    else { XSB_CHK(A(x, t1)); XSB_CHK(vec_aypx(c, n, -1.0, b, t1)); XSB_CHK(M(t1, V[0])); }
+    first = false;
+    XSB_CHK(vec_mdot(c, rg, V[0], nullptr, 0, true, scal, true));
+    XSB_CHK(vec_fetch(c, scal, 1, hcol.data()));
+    double res = sqrt(hcol[0]);
+    if (its == 0) { rnorm0 = res; ttol = fmax(rtol * rnorm0, 1e-50); }
+    if (res == 0.0 || res <= ttol) { reason = 2; break; }
+    if (its >= max_it) { reason = -3; break; }
+    XSB_CHK(vec_scale(c, n, 1.0 / res, V[0]));
+    rs[0] = res;
+    int it = 0;
+    while (!reason && it < m && its < max_it) {
+      XSB_CHK(need(it + 1));
+      double *w = V[it + 1];
+      XSB_CHK(A(V[it], t2)); XSB_CHK(M(t2, w));
+      XSB_CHK(vec_mdot(c, rg, w, V.data(), it + 1, false, scal, true));
+      XSB_CHK(vec_maxpy_dev(c, n, w, V.data(), it + 1, scal, -1.0));
+      XSB_CHK(vec_mdot(c, rg, w, nullptr, 0, true, scal + it + 1, true));
+      XSB_CHK(vec_scale_by_inv_sqrt(c, n, w, scal + it + 1));
+      XSB_CHK(vec_fetch(c, scal, it + 2, hcol.data()));
+      hcol[it + 1] = sqrt(hcol[it + 1]);
+      for (int j = 0; j < it; ++j) { double t = hcol[j]; hcol[j] = cs[j] * t + sn[j] * hcol[j + 1]; hcol[j + 1] = -sn[j] * t + cs[j] * hcol[j + 1]; }
+      const double tt = sqrt(hcol[it] * hcol[it] + hcol[it + 1] * hcol[it + 1]);
+      if (tt == 0.0) { reason = -5; break; }
+      cs[it] = hcol[it] / tt; sn[it] = hcol[it + 1] / tt;
+      rs[it + 1] = -sn[it] * rs[it]; rs[it] = cs[it] * rs[it];
+      hcol[it] = cs[it] * hcol[it] + sn[it] * hcol[it + 1]; hcol[it + 1] = 0.0;
+      res = fabs(rs[it + 1]);
+      for (int j = 0; j <= it; ++j) hh[(size_t)it * (m + 1) + j] = hcol[j];
+      it++; its++;
+      if (res <= ttol) reason = 2; else if (res >= 1e4 * rnorm0) reason = -4; else if (its >= max_it) reason = -3;
+    }
+    if (it > 0) {
+      for (int k = it - 1; k >= 0; --k) { double t = rs[k]; for (int j = k + 1; j < it; ++j) t -= hh[(size_t)j * (m + 1) + k] * y[j]; y[k] = t / hh[(size_t)k * (m + 1) + k]; }
+      CUDA_OK(cudaMemcpyAsync(scal + 64, y.data(), sizeof(double) * it, cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));   // y is a local of this frame
+      XSB_CHK(vec_maxpy_dev(c, n, x, V.data(), it, scal + 64, 1.0));
+    }
+  }
+  if (its_out) *its_out = its;
+  return 0;
+}
+}   // namespace
+
+void fsd_free(xsb_ctx c) { if (c->fsd) { delete (Fsd *)c->fsd; c->fsd = nullptr; } }
+
+int fsd_setup(xsb_ctx c)
+{
+  if (c->slab.nranks > 1) return xsb_fail(c, XSB_ERR_SUP, "the default -fs tree (GMRES + ILU(0) on A00) is implemented for one GPU; use the abf.opts tree on slabs");
+  if (c->no_A) return xsb_fail(c, XSB_ERR_SUP, "the default -fs tree factors the assembled A00 (not -xsb_matrix_free full)");
+  fsd_free(c);
+  Fsd *F = new Fsd(); c->fsd = F;
+  Options &o = c->opt; const Lattice &L = c->lat; cudaStream_t st = c->stream;
+  F->u_max_it = o.integer("saddle_fieldsplit_u_ksp_max_it", 10000); F->u_rtol = o.real("saddle_fieldsplit_u_ksp_rtol", 1e-5);
+  F->p_max_it = o.integer("saddle_fieldsplit_p_ksp_max_it", 10000); F->p_rtol = o.real("saddle_fieldsplit_p_ksp_rtol", 1e-5);
+  const std::string pk = o.str("saddle_fieldsplit_p_ksp_type", "gmres");
+  if (pk == "preonly") F->p_preonly = 1; else if (pk != "gmres") return xsb_fail(c, XSB_ERR_SUP, "-saddle_fieldsplit_p_ksp_type %s (gmres|preonly)", pk.c_str());
+  const std::string uk = o.str("saddle_fieldsplit_u_ksp_type", "gmres"), up = o.str("saddle_fieldsplit_u_pc_type", "ilu"), pp = o.str("saddle_fieldsplit_p_pc_type", "ilu");
+  if (uk != "gmres" || up != "ilu" || (pp != "ilu" && pp != "bjacobi")) return xsb_fail(c, XSB_ERR_SUP, "default -fs tree: fieldsplit_u gmres+ilu, fieldsplit_p gmres|preonly + ilu");
+  // scalar CSR of A00
+  const Baij &B = c->A00; const int bs = B.bs; Csr &S = F->A00s;
+  S.n = S.m = B.nb * bs; S.nnz = B.nblk * bs * bs;
+  XSB_CHK(dev_alloc(c, &S.ia, (size_t)S.n + 1)); XSB_CHK(dev_alloc(c, &S.ja, (size_t)S.nnz)); XSB_CHK(dev_alloc(c, &S.a, (size_t)S.nnz));
+  if (bs == 3) k_baij_scalar<3><<<(B.nb + 256) / 256, 256, 0, st>>>(B.nb, B.ia, B.ja, B.a, S.ia, S.ja, S.a);
+  else k_baij_scalar<2><<<(B.nb + 256) / 256, 256, 0, st>>>(B.nb, B.ia, B.ja, B.a, S.ia, S.ja, S.a);
+  KERNEL_OK();
+  XSB_CHK(gilu_setup(c, S, F->ilu_u));
+  XSB_CHK(ilu_setup(c));   // ILU(0) of Mpscaled (lattice wavefronts, xsb_ilu.cu)
+  XSB_CHK(dev_alloc(c, &F->u_t1, (size_t)L.nu)); XSB_CHK(dev_alloc(c, &F->u_t2, (size_t)L.nu)); XSB_CHK(dev_alloc(c, &F->u_rhs, (size_t)L.nu)); XSB_CHK(dev_alloc(c, &F->u_sol, (size_t)L.nu));
+  XSB_CHK(dev_alloc(c, &F->p_t1, (size_t)L.np)); XSB_CHK(dev_alloc(c, &F->p_t2, (size_t)L.np)); XSB_CHK(dev_alloc(c, &F->p_tmp, (size_t)L.np));
+  return 0;
+}
+
+// PCApply_FieldSplit_Schur, UPPER, with the default sub-solvers
+int fsd_apply(xsb_ctx c, const double *r, double *z)
+{
+  Fsd *F = (Fsd *)c->fsd; const Lattice &L = c->lat; const int64_t nu = L.nu, np = L.np;
+  Epilogue plain;
+  Op A00 = [&](const double *x, double *y) { return spmv_baij(c, c->A00, x, y, plain); };
+  Op Mu = [&](const double *x, double *y) { return gilu_apply(c, F->ilu_u, x, y); };
+  Op Mp = [&](const double *x, double *y) { return ilu_apply(c, x, y); };
+  auto ksp_u = [&](const double *rhs, double *sol) { F->n_ksp_u++; return gmres_left(c, nu, A00, Mu, rhs, sol, F->u_rtol, F->u_max_it, 30, F->Vu, F->u_t1, F->u_t2, c->scal, nullptr); };
+  double *yu = z, *yp = z + nu;
+  if (F->p_preonly) XSB_CHK(Mp(r + nu, yp));
+  else {
+    // S v = A11 v - A10 KSP_u(A01 v): MatSchurComplement with a nested velocity solve per application
+    Op S = [&](const double *v, double *y) {
+      XSB_CHK(spmv_csr(c, c->A01, v, F->u_rhs));
+      XSB_CHK(ksp_u(F->u_rhs, F->u_sol));
+      XSB_CHK(spmv_csr(c, c->A10, F->u_sol, F->p_tmp));
+      XSB_CHK(spmv_csr(c, c->A11, v, y));
+      return vec_axpy(c, np, -1.0, F->p_tmp, y);
+    };
+    XSB_CHK(gmres_left(c, np, S, Mp, r + nu, yp, F->p_rtol, F->p_max_it, 30, F->Vp, F->p_t1, F->p_t2, c->scal + 96, nullptr));
+  }
+  XSB_CHK(spmv_csr(c, c->A01, yp, F->u_rhs));
+  XSB_CHK(vec_aypx(c, nu, -1.0, r, F->u_rhs));      // x_u - A01 y_p
+  return ksp_u(F->u_rhs, yu);
+}

@@ -121,6 +121,7 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reaso
   if (c->so.pc_type == 1) return vec_pmult(c, L.n, c->idiagA, r, z);
   if (c->so.pc_type == 0) return vec_copy(c, L.n, r, z);
   if (c->so.pc_type == 3) return mmg_apply(c, r, z);
+  if (c->so.pc_type == 4) return fsd_apply(c, r, z);
   // PCApply_FieldSplit_Schur, PC_FIELDSPLIT_SCHUR_FACT_UPPER
   double *yp = z + L.nu;
   if (c->so.p_pc == 0) XSB_CHK(ilu_apply(c, r + L.nu + c->own_p.off0, yp + c->own_p.off0)); else XSB_CHK(vec_pmult(c, L.np, c->mp_idiag, r + L.nu, yp));
@@ -148,10 +149,13 @@ static int read_solver_options(xsb_ctx c)
   if (mg) {
     s.pc_type = 3;   // monolithic PCMG on the saddle operator (xsb_mmg.cu)
     if (o.flag("fs_coarse")) return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse (fieldsplit coarse solver) is not implemented");
+  } else if (fs && o.str("saddle_fieldsplit_u_pc_type", "") != "mg") {
+    s.pc_type = 4;   // plain -fs: PETSc's default sub-solvers (GMRES + ILU(0) on A00, nested Schur solves); validated in fsd_setup (xsb_fs.cu)
+    o.has("saddle_fieldsplit_u_ksp_type"); o.has("saddle_fieldsplit_p_ksp_type"); o.has("saddle_fieldsplit_u_ksp_max_it"); o.has("saddle_fieldsplit_p_pc_type");
   } else if (fs) {
     s.pc_type = 2;
-    if (o.str("saddle_fieldsplit_u_pc_type", "") != "mg" || o.str("saddle_fieldsplit_u_ksp_type", "") != "gcr" || o.str("saddle_fieldsplit_p_ksp_type", "") != "preonly")
-      return xsb_fail(c, XSB_ERR_SUP, "-fs is supported with the abf.opts tree: fieldsplit_u gcr+mg, fieldsplit_p preonly");
+    if (o.str("saddle_fieldsplit_u_ksp_type", "") != "gcr" || o.str("saddle_fieldsplit_p_ksp_type", "") != "preonly")
+      return xsb_fail(c, XSB_ERR_SUP, "-fs with -saddle_fieldsplit_u_pc_type mg is supported as the abf.opts tree: fieldsplit_u gcr+mg, fieldsplit_p preonly");
     if (o.str("saddle_fieldsplit_u_mg_levels_ksp_type", "chebyshev") != "chebyshev" || o.str("saddle_fieldsplit_u_mg_levels_pc_type", "jacobi") != "jacobi")
       return xsb_fail(c, XSB_ERR_SUP, "MG smoother must be chebyshev/jacobi");
     o.has("saddle_fieldsplit_u_pc_mg_galerkin"); o.has("saddle_fieldsplit_u_mg_levels_ksp_norm_type"); o.has("saddle_fieldsplit_u_mg_coarse_pc_factor_mat_solver_type");
@@ -213,7 +217,7 @@ int ksp_release(xsb_ctx c)
 {
   CUDA_OK(cudaStreamSynchronize(c->stream));
   mg_graphs_release(c);
-  mmg_free(c);
+  mmg_free(c); fsd_free(c);
   dev_free_phase(c, 1);
   c->red = c->scal = nullptr; c->w_t1 = c->w_t2 = c->xdev = c->bdev = c->idiagA = c->gcr_r = c->fs_tu = nullptr;
   c->mp_lu = c->mp_idiag = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
@@ -239,6 +243,7 @@ int ksp_setup(xsb_ctx c)
   XSB_CHK(dev_alloc(c, &c->w_t1, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->w_t2, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->xdev, (size_t)L.n)); XSB_CHK(dev_alloc(c, &c->bdev, (size_t)L.n));
   if (c->so.pc_type == 1) { XSB_CHK(dev_alloc(c, &c->idiagA, (size_t)L.n)); XSB_CHK(csr_diag_inv(c, c->A, c->idiagA)); }
   if (c->so.pc_type == 3) XSB_CHK(mmg_setup(c));
+  if (c->so.pc_type == 4) XSB_CHK(fsd_setup(c));
   if (c->so.pc_type == 2) {
     if (c->so.matrix_free) XSB_CHK(mf_setup(c));
     XSB_CHK(mg_setup(c));

@@ -354,6 +354,36 @@ def test_golden_monolithic_mg_output_is_identical(kat, name):
     assert s.iterations() == (len(c["residuals"]) - 1, 2)
 
 
+# ------------------------------------------------------------------ plain -fs tree: PETSc's default sub-solvers (xsb_fs.cu)
+@pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1"])
+def test_golden_plain_fs_output_is_identical(kat, name):
+    """`-fs` without abf.opts (exSaddle.c:303-322, Makefile:282, 347, 396, 480): GMRES + fieldsplit Schur-upper with GMRES + ILU(0)
+    of A00 and of Mpscaled, a nested velocity solve inside every Schur-complement product.  The program output (banner, residual
+    history as printed by -saddle_ksp_monitor_short, converged-reason line where asked, diagnostics) diffs clean against testref."""
+    c, text, s, x = _run(kat, name)
+    ref = list(c["banner"]) + ["  Residual norms for saddle_ solve."] + ["%3d KSP Residual norm %s" % (i, t) for i, t in enumerate(c["residuals_text"])]
+    got = [l.rstrip() for l in text.rstrip("\n").split("\n")]
+    if "-saddle_ksp_converged_reason" in c["options"]:
+        assert got[len(ref)].startswith("Linear saddle_ solve")
+        got = got[:len(ref)] + got[len(ref) + 1:]
+    assert got == ref + [l.rstrip() for l in c["diagnostics"]]
+
+
+@pytest.mark.parametrize("opts,nsd,lame", [("-model 6 -mx 3 -my 4 -mz 2 -eta1 10 -fs", 3, False), ("-model 0 -mx 5 -my 4 -fs -saddle_fieldsplit_p_ksp_type preonly", 2, False),
+                                           ("-model 8 -mx 3 -fs -saddle_fieldsplit_u_ksp_max_it 7", 3, True)])
+def test_plain_fs_tree_matches_oracle(opts, nsd, lame):
+    from oracle.oracle_fs import FieldSplitDefault
+    g = X.ExSaddle(opts, nsd=nsd, lame=lame).assemble().ksp_setup()
+    x = g.solve()
+    F = FieldSplitDefault(opts, nsd=nsd, lame=lame)
+    xo, its, reason, hist = F.solve()
+    assert g.iterations() == (its, reason)
+    h = g.history(); ho = np.array(hist)
+    assert np.max(np.abs(h - ho)) <= 1e-8 * ho[0]
+    assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+    g.close()
+
+
 @pytest.mark.parametrize("opts,nsd,lame", [("-model 1 -mx 4 -my 8 -mz 4 -mg -nlevels 2", 3, False), ("-model 0 -mx 16 -mg -nlevels 4", 2, False),
                                            ("-model 12 -mx 4 -mu1 10 -mg -nlevels 2", 3, True)])
 def test_monolithic_mg_matches_oracle(opts, nsd, lame):
