@@ -1,4 +1,7 @@
-// xsb_mf.cu -- matrix-free, sum-factorised Q2 apply of the velocity block A00 (K4 of SURVEY 2.1).
+// xsb_mf.cu -- matrix-free, sum-factorised Q2 apply of the velocity block A00 (K4 of SURVEY 2.1): set-up, dispatch and the
+// 8-colour kernel of round 1.  The production kernel is the one-pass TMA-staged kernel in xsb_mf1p.cu (-xsb_mf_kernel 4,
+// default); the colour kernel below (-xsb_mf_kernel 3) is kept as the reference point of the A/B timings and as the path for
+// vectors that are not 16-byte aligned (the bulk copies of the one-pass kernel need that).
 //
 // y = A00 x without reading the 10.4 GB assembled block: per element, gather the 27 x 3 nodal values, evaluate
 // grad u at the 27 Gauss points by sum factorisation (three 1-D contractions instead of a 27 x 27 one),
@@ -36,98 +39,6 @@ void mf_tab_scaled(const Lattice &L, MfTabS &TS)
 }
 
 #define FULL 0xffffffffu
-// values of `v` held by the 3 lanes of my row (same b, a = 0,1,2) / my column (same a, b = 0,1,2)
-#define ROW3(v, o) { o[0] = __shfl_sync(FULL, v, rowb); o[1] = __shfl_sync(FULL, v, rowb + 1); o[2] = __shfl_sync(FULL, v, rowb + 2); }
-#define COL3(v, o) { o[0] = __shfl_sync(FULL, v, colb); o[1] = __shfl_sync(FULL, v, colb + 3); o[2] = __shfl_sync(FULL, v, colb + 6); }
-#define DOT3(c, v) ((c)[0] * (v)[0] + (c)[1] * (v)[1] + (c)[2] * (v)[2])
-
-__global__ void __launch_bounds__(128) mf_a00_kernel(Lattice L, int colour, double ihx, double ihy, double ihz, double detJ,
-                                                     const double *__restrict__ eta, const unsigned char *__restrict__ isbc,
-                                                     const double *__restrict__ x, double *__restrict__ y)
-{
-  const int lane = threadIdx.x & 31;
-  const int g = lane / 9, r = lane - 9 * g, a = r % 3, b = r / 3;
-  const bool active = lane < 27;
-  const int rowb = 9 * g + 3 * b, colb = 9 * g + a;
-  const int ci = colour & 1, cj = (colour >> 1) & 1, ck = (colour >> 2) & 1;
-  const int nei = (L.mx - ci + 1) / 2, nej = (L.my - cj + 1) / 2, nek = (L.mz - ck + 1) / 2;
-  const int64_t nelc = (int64_t)nei * nej * nek;
-  const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t t = wg * 3 + g;
-  const bool valid = active && t < nelc;
-  // lane-specific 1-D coefficients (forward: rows of N/D at my Gauss index; transpose: columns at my node index)
-  double Na[3], Da[3], Nb[3], Db[3], NaT[3], DaT[3], NbT[3], DbT[3];
-#pragma unroll
-  for (int n = 0; n < 3; ++n) {
-    Na[n] = c_tab.N[a][n]; Da[n] = c_tab.D[a][n]; Nb[n] = c_tab.N[b][n]; Db[n] = c_tab.D[b][n];
-    NaT[n] = c_tab.N[n][a]; DaT[n] = c_tab.D[n][a]; NbT[n] = c_tab.N[n][b]; DbT[n] = c_tab.D[n][b];
-  }
-  int ei = 0, ej = 0, ek = 0;
-  if (valid) { ei = 2 * (int)(t % nei) + ci; ej = 2 * (int)((t / nei) % nej) + cj; ek = 2 * (int)(t / ((int64_t)nei * nej)) + ck; }
-  const int64_t e = ei + (int64_t)ej * L.mx + (int64_t)ek * L.mx * L.my;
-  const int64_t node0 = (2 * ei + a) + (int64_t)(2 * ej + b) * L.NX + (int64_t)(2 * ek) * L.NX * L.NY, kstride = (int64_t)L.NX * L.NY;
-  // gather (Dirichlet columns masked: MatZeroRowsColumns)
-  double U[3][3];   // [comp][k]
-  double fac[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int64_t i0 = 3 * (node0 + k * kstride);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) U[c][k] = (valid && !isbc[i0 + c]) ? __ldg(x + i0 + c) : 0.0;
-    fac[k] = valid ? __ldg(eta + e * 27 + a + 3 * b + 9 * k) * (c_tab.w[a] * c_tab.w[b] * c_tab.w[k]) * detJ : 0.0;   // eta w |J| at (a,b,k)
-  }
-  // forward: G[c][d][q] = d u_c / d x_d at Gauss points (a,b,q)
-  double G[3][3][3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double tN[3], tD[3], tNN[3], tND[3], tDN[3], v[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { ROW3(U[c][k], v); tN[k] = DOT3(Na, v); tD[k] = DOT3(Da, v); }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { COL3(tN[k], v); tNN[k] = DOT3(Nb, v); tND[k] = DOT3(Db, v); COL3(tD[k], v); tDN[k] = DOT3(Nb, v); }
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      G[c][0][q] = ihx * (c_tab.N[q][0] * tDN[0] + c_tab.N[q][1] * tDN[1] + c_tab.N[q][2] * tDN[2]);
-      G[c][1][q] = ihy * (c_tab.N[q][0] * tND[0] + c_tab.N[q][1] * tND[1] + c_tab.N[q][2] * tND[2]);
-      G[c][2][q] = ihz * (c_tab.D[q][0] * tNN[0] + c_tab.D[q][1] * tNN[1] + c_tab.D[q][2] * tNN[2]);
-    }
-  }
-  // Gauss-point work: sigma_cd = eta w |J| (G_cd + G_dc), pre-scaled by 1/h_d for the transposed derivative
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const double f = fac[q];
-    const double sxx = f * (G[0][0][q] + G[0][0][q]), syy = f * (G[1][1][q] + G[1][1][q]), szz = f * (G[2][2][q] + G[2][2][q]);
-    const double sxy = f * (G[0][1][q] + G[1][0][q]), sxz = f * (G[0][2][q] + G[2][0][q]), syz = f * (G[1][2][q] + G[2][1][q]);
-    G[0][0][q] = ihx * sxx; G[0][1][q] = ihy * sxy; G[0][2][q] = ihz * sxz;
-    G[1][0][q] = ihx * sxy; G[1][1][q] = ihy * syy; G[1][2][q] = ihz * syz;
-    G[2][0][q] = ihx * sxz; G[2][1][q] = ihy * syz; G[2][2][q] = ihz * szz;
-  }
-  // transpose: Y[c][k] at node (a,b,k)
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    double rDN[3], rND[3], rNN[3], qA[3], qB[3], v[3], Y[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      rDN[k] = c_tab.N[0][k] * G[c][0][0] + c_tab.N[1][k] * G[c][0][1] + c_tab.N[2][k] * G[c][0][2];
-      rND[k] = c_tab.N[0][k] * G[c][1][0] + c_tab.N[1][k] * G[c][1][1] + c_tab.N[2][k] * G[c][1][2];
-      rNN[k] = c_tab.D[0][k] * G[c][2][0] + c_tab.D[1][k] * G[c][2][1] + c_tab.D[2][k] * G[c][2][2];
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      COL3(rDN[k], v); qB[k] = DOT3(NbT, v);
-      COL3(rND[k], v); qA[k] = DOT3(DbT, v);
-      COL3(rNN[k], v); qA[k] += DOT3(NbT, v);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { ROW3(qA[k], v); Y[k] = DOT3(NaT, v); ROW3(qB[k], v); Y[k] += DOT3(DaT, v); }
-    // scatter: same-colour elements share no node, so a plain read-modify-write is race free
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int64_t i0 = 3 * (node0 + k * kstride) + c;
-      if (valid && !isbc[i0]) y[i0] += Y[k];
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // Version 2: 3 lanes per element (10 elements per warp).  Lane `a` owns the x-index a of the element: the
@@ -326,11 +237,12 @@ int mf_setup(xsb_ctx c)
   MfTab T; host_mf_tab(T);
   CUDA_OK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, c->stream));
   if (!c->mf_tmp) XSB_CHK(dev_alloc(c, &c->mf_tmp, (size_t)c->lat.nu));
-  c->so.mf_kernel = c->opt.integer("xsb_mf_kernel", 4);   // 4: one-pass TMA-staged kernel (xsb_mf1p.cu); 1: 9 lanes per element, 8 colour passes; 2, 3: 3 lanes per element, preloaded / reduction scatter
+  c->so.mf_kernel = c->opt.integer("xsb_mf_kernel", 4);   // 4: one-pass TMA-staged kernel (xsb_mf1p.cu); 3: 8 colour passes, 3 lanes per element, reduction scatter
   c->so.mf_tile = c->opt.integer("xsb_mf_tile", 0);
   c->so.mf_chunk = c->opt.integer("xsb_mf_chunk", 0);     // element layers per z-chunk (0 = no chunking)
   c->so.mf_reverse = c->opt.integer("xsb_mf_reverse", 1); // alternate the sweep direction of successive colour launches
-  if (c->so.mf_kernel < 1 || c->so.mf_kernel > 4) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_kernel must be 1 .. 4");
+  if (c->so.mf_kernel != 3 && c->so.mf_kernel != 4) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_kernel must be 4 (one-pass kernel) or 3 (8-colour kernel)");
+  if (c->so.mf_tile != 0 && c->so.mf_tile != 1) return xsb_fail(c, XSB_ERR_ARG, "-xsb_mf_tile must be 0 (16 x 5 elements, one CTA per SM) or 1 (8 x 5, two CTAs per SM)");
   if (!c->mf_bcnode) {
     XSB_CHK(dev_alloc(c, &c->mf_bcnode, (size_t)c->lat.nun));
     mf_bcnode_kernel<<<(unsigned)((c->lat.nun + 255) / 256), 256, 0, c->stream>>>(c->lat.nun, c->isbc, c->mf_bcnode); KERNEL_OK();
@@ -348,10 +260,8 @@ int mf_a00_apply_raw(xsb_ctx c, const double *x, double *y)
 {
   XSB_CHK(mf_setup(c));
   if (!c->mf_bczero) { const int kp = c->phase; c->phase = 2; int rc = dev_alloc(c, &c->mf_bczero, (size_t)c->lat.nun); c->phase = kp; if (rc) return rc; }   // dev_alloc zero-fills
-  Epilogue ep; const int keep = c->so.mf_kernel; if (c->so.mf_kernel == 1) c->so.mf_kernel = 3;   // v1 reads the per-dof mask
-  int rc = mf_apply_core(c, x, y, ep, nullptr, c->mf_bczero);
-  c->so.mf_kernel = keep;
-  return rc;
+  Epilogue ep;
+  return mf_apply_core(c, x, y, ep, nullptr, c->mf_bczero);
 }
 static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &ep, const unsigned char *isbc, const unsigned char *bcnode)
 {
@@ -363,20 +273,12 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
   int zlo, zhi; mf_layer_range(c, isbc != nullptr, &zlo, &zhi);
   if (c->so.mf_kernel == 4) {
     const uintptr_t al = (uintptr_t)x | (uintptr_t)ep.b | (uintptr_t)ep.idiag | (uintptr_t)ep.pkm1;
-    if (al & 15) return xsb_fail(c, XSB_ERR_ARG, "one-pass element kernel: vectors must be 16-byte aligned");
-    return mf1p_apply(c, x, y, ep, bcnode, zlo, zhi);
+    if (!(al & 15)) return mf1p_apply(c, x, y, ep, bcnode, zlo, zhi);
+    // vectors off the 16-byte grid (a caller's sub-vector): the colour kernel below has no alignment requirement
   }
   CUDA_OK(cudaMemsetAsync(c->mf_tmp, 0, sizeof(double) * L.nu, st));
   MfTabS TS; mf_tab_scaled(L, TS);
-  if (c->so.mf_kernel == 1) {
-    for (int col = 0; col < 8; ++col) {
-      const int ci = col & 1, cj = (col >> 1) & 1, ck = (col >> 2) & 1;
-      const int64_t ne = (int64_t)((L.mx - ci + 1) / 2) * ((L.my - cj + 1) / 2) * ((L.mz - ck + 1) / 2);
-      if (ne <= 0) continue;
-      const int64_t warps = (ne + 2) / 3, blocks = (warps * 32 + 127) / 128;
-      mf_a00_kernel<<<(unsigned)blocks, 128, 0, st>>>(L, col, 1.0 / L.hu[0], 1.0 / L.hu[1], 1.0 / L.hu[2], detJ, eta, isbc, x, c->mf_tmp); KERNEL_OK();
-    }
-  } else {
+  {
     // optional z-chunks of element layers (-xsb_mf_chunk): the 8 colours run chunk by chunk so a chunk's x / y planes stay in L2
     int chunk = c->so.mf_chunk;
     if (chunk <= 0) chunk = L.mz;
@@ -391,8 +293,7 @@ static int mf_apply_core(xsb_ctx c, const double *x, double *y, const Epilogue &
         if (ne <= 0) continue;
         const int64_t warps = (ne + 9) / 10; int64_t blocks = (warps + 3) / 4;
         const int rev = c->so.mf_reverse ? (launch++) & 1 : 0;
-        if (c->so.mf_kernel == 2) mf_a00_kernel_v2<1><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, bcnode, x, c->mf_tmp);
-        else mf_a00_kernel_v2<0><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, bcnode, x, c->mf_tmp);
+        mf_a00_kernel_v2<0><<<(unsigned)blocks, 128, 0, st>>>(L, col, kz0, kz1, rev, TS, detJ, eta, bcnode, x, c->mf_tmp);
         KERNEL_OK();
       }
     }

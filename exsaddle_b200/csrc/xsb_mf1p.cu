@@ -1,16 +1,17 @@
 // xsb_mf1p.cu -- one-pass, shared-memory / TMA-staged matrix-free Q2 apply of the velocity block (K4 of SURVEY 2.1).
 //
-// y = epilogue(A00 x) with ONE pass over x, y and the viscosity field (femixedspace.c:2491-2561 applied element by
-// element, never assembled).  Replaces round 1's memset + 8 colour launches + epilogue (3.6 x the algorithmic DRAM
-// traffic: every colour pass re-read x and read-modify-wrote the accumulator).
+// y = epilogue(A00 x) with ONE pass over x, y, the viscosity field and the epilogue operands (femixedspace.c:2491-2561
+// applied element by element, never assembled).  Replaces round 1's memset + 8 colour launches + epilogue (3.6 x the
+// algorithmic DRAM traffic: every colour pass re-read x and read-modify-wrote the accumulator; now 1.2 x).
 //
 //   * The element lattice is cut into columns of TI x TJ elements; the (column, element layer) pairs are linearised
 //     (layers fastest) and split evenly over one persistent CTA per SM.  A CTA marches through its layers bottom-up.
-//   * Node planes of x (and of the epilogue operands b, 1/diag, p_{k-1}) are brought into shared memory by bulk
-//     asynchronous copies (cp.async.bulk global -> shared, completion on an mbarrier), one copy per node row of the
-//     tile, two layers ahead of the arithmetic; the three planes of a layer live in a ring of five.
+//   * Node planes of x, the viscosity of the layer and the epilogue operands (b, 1/diag, p_{k-1}) are brought into shared
+//     memory by bulk asynchronous copies (cp.async.bulk global -> shared, SASS UBLKCP, completion on an mbarrier with
+//     expect_tx), one copy per node row of the tile, a layer ahead of their use; the three x planes of a layer live in a
+//     ring of five.  Copies are issued by single lanes with uniform operands, spread over the warps.
 //   * Arithmetic: 3 lanes per element (lane a owns the x-index a), sum-factorised forward / transposed contractions in
-//     registers, the x-contraction through warp shuffles -- the element kernel of round 1, now fed from shared memory.
+//     registers, the x-contraction through warp shuffles; zero / unit entries of the 1-D tables are skipped (exact).
 //   * Each element writes its 81 outputs to an element-local slot of shared memory (no atomics, no colouring).  After a
 //     block barrier the NODE PHASE sums, for every node of the two planes that are complete in z, the contributions of
 //     the <= 4 (+ the carried top plane of the layer below) elements around it in a fixed order, applies the Dirichlet
@@ -19,12 +20,18 @@
 //     part[slot][dof] (slot = parity of the tile in x, y and the z side); a small second kernel adds the <= 8 partial
 //     sums of such a node in a fixed order and applies the same epilogue.  ~14 % of the nodes at 64^3.
 // Summation order is fixed by the geometry, not by timing: the result is bit-reproducible run to run.
+//
+// Measured and dropped in round 2 (profiles/r02_summary.md): two / three / four smaller CTAs per SM (instruction-cache misses
+// and spills cost more than the occupancy gains), operands read from global memory in the node phase (long-scoreboard stalls),
+// a deferred node phase with one barrier per layer (all warps still hit it together), Dirichlet masking applied to the staged
+// planes instead of in registers.
 #include "xsb.h"
 
 namespace {
 // Tile configuration: TI x TJ elements per tile layer (a multiple of 10: one warp per 10 elements), CPS CTAs resident per SM.
-template <int TI_, int TJ_, int CPS_> struct Cfg {
+template <int TI_, int TJ_, int CPS_, bool STAGE_> struct Cfg {
   static constexpr int TI = TI_, TJ = TJ_, CPS = CPS_;
+  static constexpr bool STAGE = STAGE_;                // epilogue operands (b, 1/diag, p_{k-1}) staged in shared memory by bulk copies, or read from global in the node phase
   static constexpr int NEL = TI * TJ;                  // elements per tile layer
   static constexpr int NTHR = (NEL / 10) * 32;
   static constexpr int BX = 2 * TI + 1, BY = 2 * TJ + 1;  // nodes of a tile plane
@@ -32,17 +39,17 @@ template <int TI_, int TJ_, int CPS_> struct Cfg {
   static constexpr int ROW_BYTES = ROWP * 8;
   static constexpr int SLOT = BY * ROWP;               // doubles per staged node plane
   static constexpr int NXS = 5;                        // ring of x planes: 3 in use + 2 in flight
-  static constexpr int NMS = 7;                        // ring of Dirichlet-bit planes: the deferred node phase still reads 2 older planes
   static constexpr int YS = 83;                        // element stride of the element-local output buffer (81 used; 83 = 3 mod 16: conflict-free)
-  static constexpr int MS_BYTES = ((NMS * BY * BX + 15) / 16) * 16;
+  static constexpr int MS_BYTES = ((NXS * BY * BX + 15) / 16) * 16;
   static constexpr int MPT = (2 * BY * BX + NTHR - 1) / NTHR;   // Dirichlet bytes of the two prefetched planes per thread
+  static constexpr int NES = STAGE ? 6 : 0;            // staged operand planes: 3 vectors x the 2 planes a layer completes
   static constexpr int EROWP = TI * 27 + 2;            // doubles per staged viscosity row (TI elements x 27 Gauss points + alignment shift)
   static constexpr int ESLOT = TJ * EROWP;             // one element layer of the tile
-  static constexpr size_t SMEM_BYTES = sizeof(double) * ((size_t)NXS * SLOT + 2 * ESLOT + 2 * (size_t)NEL * YS + BY * BX * 3) + MS_BYTES + 64;
+  static constexpr size_t SMEM_BYTES = sizeof(double) * ((size_t)NXS * SLOT + NES * SLOT + 2 * ESLOT + (size_t)NEL * YS + BY * BX * 3) + MS_BYTES + 64;
   static_assert(NEL % 10 == 0 && ROW_BYTES % 16 == 0 && (SLOT * 8) % 16 == 0 && EROWP % 2 == 0 && TI % 2 == 0, "tile: multiple of 10 elements, even TI, 16-byte granular bulk copies");
 };
-typedef Cfg<16, 5, 1> CfgWide;    // 80 elements, 256 threads, one CTA per SM (196 KB of shared memory)
-typedef Cfg<8, 5, 2> CfgTwo;      // 40 elements, 128 threads, two CTAs per SM (99 KB each)
+typedef Cfg<16, 5, 1, true> CfgWide;    // 80 elements, 256 threads, one CTA per SM (157 KB of shared memory)
+typedef Cfg<8, 5, 2, true> CfgTwo;      // 40 elements, 128 threads, two CTAs per SM (80 KB each): one CTA's node phase overlaps the other's arithmetic
 
 struct Args {
   Lattice L;
@@ -105,127 +112,20 @@ __device__ __forceinline__ void touching(int l, int n, int &e0, int &loc0, int &
   else { e0 = lo; loc0 = 2; cnt = 2; }   // second element: e0 + 1 with local node 0
 }
 
-// Arithmetic of one element layer: 3 lanes per element (lane a owns the x-index a), 10 elements per warp.  Reads the staged
-// planes 2s .. 2s+2 of x and the staged viscosity of layer s, writes the element's 81 outputs to its slot of `yl`.
-template <class C>
-__device__ __forceinline__ void element_phase(const MfTabS &T, const double *xs, const double *etas, double *yl, int s, int nti, int nelt, int ej0,
-                                              int warp, int lane, int pbx, int pbe, int mx, int my, double wa, const double (&Nr)[3], const double (&Dr)[3], int src1, int src2)
-{
-  constexpr int ROWP = C::ROWP, SLOT = C::SLOT, NXS = C::NXS, YS = C::YS, EROWP = C::EROWP, ESLOT = C::ESLOT;
-  if (10 * warp >= nelt) return;
-  const int g = lane / 3, a = lane - 3 * g;
-  const int t = 10 * warp + g;
-  const bool valid = lane < 30 && t < nelt;
-  const int tv = valid ? t : 0;
-  const int tj = tv / nti, ti = tv - tj * nti;
-  // x is read from shared memory where it is used (Dirichlet entries already zero)
-  const double *xp[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) xp[k] = xs + ((2 * s + k) % NXS) * SLOT + (2 * tj) * ROWP + 3 * (2 * ti + a);
-  double E[6][3][3];     // [sym slot][b][q]; every entry is first written by assignment, no zero fill
-  // ---- forward: E_cd = d u_c / d x_d + d u_d / d x_c at my 9 Gauss points
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double tN[3], tD[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        // alignment shift of row 2 tj + j of plane 2 s + k: (pbx + i0 + j0 + row + plane) & 1 = pbx ^ ((j + k) & 1), i0 / j0 / 2 tj / 2 s being even
-        const double u = valid ? xp[k][j * ROWP + c + (((j + k) & 1) ? (pbx ^ 1) : pbx)] : 0.0;
-        const double u1 = shfl_d(u, src1), u2 = shfl_d(u, src2);
-        tN[j] = Nr[0] * u + Nr[1] * u1 + Nr[2] * u2;
-        tD[j] = Dr[0] * u + Dr[1] * u1 + Dr[2] * u2;
-      }
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        // 1-D tables at the middle Gauss point (xi = 0): N[1] = (0, 1, 0), D[1] = (-d, 0, d) -- the zero terms are skipped
-        // (exact: they add 0), the unit coefficient needs no multiply
-        const double gx = b == 1 ? tD[1] : T.N[b][0] * tD[0] + T.N[b][1] * tD[1] + T.N[b][2] * tD[2];                          // D in x, N in y
-        const double gy = b == 1 ? T.Dy[1][0] * tN[0] + T.Dy[1][2] * tN[2] : T.Dy[b][0] * tN[0] + T.Dy[b][1] * tN[1] + T.Dy[b][2] * tN[2];   // N in x, D in y
-        const double gz = b == 1 ? tN[1] : T.N[b][0] * tN[0] + T.N[b][1] * tN[1] + T.N[b][2] * tN[2];                          // N in x, N in y (D in z below)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          // slot (c,d) is first touched by the component min(c,d) at its first contributing k (k = 0, or k = 1 for q = 1 with N);
-          // diagonal slots get one contribution per k, off-diagonal ones two (G_cd from c, G_dc from d)
-#define XSB_ACC(slot, first, val) do { if (first) E[slot][b][q] = (val); else E[slot][b][q] += (val); } while (0)
-          if (q == 1) { if (k == 1) { XSB_ACC(sym_idx(c, 0), c <= 0, gx); XSB_ACC(sym_idx(c, 1), c <= 1, gy); } }
-          else { XSB_ACC(sym_idx(c, 0), c <= 0 && k == 0, T.N[q][k] * gx); XSB_ACC(sym_idx(c, 1), c <= 1 && k == 0, T.N[q][k] * gy); }
-          if (!(q == 1 && k == 1)) XSB_ACC(sym_idx(c, 2), c <= 2 && k == 0, T.Dz[q][k] * gz);
-#undef XSB_ACC
-        }
-      }
-    }
-  }
-  // ---- Gauss points: sigma = eta w |J| (G + G^T); diagonal slots hold G_cc once, so double them.  Viscosity of my 9 points
-  // from the staged layer (row of element row tj; the copy started at the 16-byte boundary below its first value)
-  const double *etap = etas + (s & 1) * ESLOT + tj * EROWP + ti * 27 + a + ((pbe + mx * ((ej0 + tj) + my * s)) & 1);
-#pragma unroll
-  for (int b = 0; b < 3; ++b)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const double f = etap[3 * b + 9 * q] * (wa * (T.w[b] * T.w[q]));
-      E[0][b][q] = f * (E[0][b][q] + E[0][b][q]); E[1][b][q] = f * (E[1][b][q] + E[1][b][q]); E[2][b][q] = f * (E[2][b][q] + E[2][b][q]);
-      E[3][b][q] *= f; E[4][b][q] *= f; E[5][b][q] *= f;
-    }
-  // ---- transpose: the element's contribution to y_c at its node (a, j, k), stored element-locally
-  double *yo = yl + tv * YS + a;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double rx[3], ry[3], rz[3];   // index b
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const double *e0 = E[sym_idx(c, 0)][b], *e1 = E[sym_idx(c, 1)][b], *e2 = E[sym_idx(c, 2)][b];
-        if (k == 1) {   // N[1][1] = 1, Dz[1][1] = 0
-          rx[b] = T.N[0][1] * e0[0] + e0[1] + T.N[2][1] * e0[2];
-          ry[b] = T.N[0][1] * e1[0] + e1[1] + T.N[2][1] * e1[2];
-          rz[b] = T.Dz[0][1] * e2[0] + T.Dz[2][1] * e2[2];
-        } else {        // N[1][k] = 0
-          rx[b] = T.N[0][k] * e0[0] + T.N[2][k] * e0[2];
-          ry[b] = T.N[0][k] * e1[0] + T.N[2][k] * e1[2];
-          rz[b] = T.Dz[0][k] * e2[0] + T.Dz[1][k] * e2[1] + T.Dz[2][k] * e2[2];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double qD, qN;
-        if (j == 1) {
-          qD = T.N[0][1] * rx[0] + rx[1] + T.N[2][1] * rx[2];                                              // pairs with D in x
-          qN = T.Dy[0][1] * ry[0] + T.Dy[2][1] * ry[2] + T.N[0][1] * rz[0] + rz[1] + T.N[2][1] * rz[2];    // pairs with N in x
-        } else {
-          qD = T.N[0][j] * rx[0] + T.N[2][j] * rx[2];
-          qN = T.Dy[0][j] * ry[0] + T.Dy[1][j] * ry[1] + T.Dy[2][j] * ry[2] + T.N[0][j] * rz[0] + T.N[2][j] * rz[2];
-        }
-        // reduce-scatter over the 3 lanes: my contribution to node i = (a+r)%3 is s_r
-        const double sA = Nr[0] * qN + Dr[0] * qD, sB = Nr[1] * qN + Dr[1] * qD, sC = Nr[2] * qN + Dr[2] * qD;
-        const double Y = sA + shfl_d(sB, src2) + shfl_d(sC, src1);
-        if (valid) yo[c * 27 + 3 * j + 9 * k] = Y;
-      }
-    }
-  }
-}
-
-// The persistent one-pass kernel.  Per element layer s of a segment, ONE block barrier:
-//   top      wait for the bulk copies of layer s (x planes, viscosity), zero the Dirichlet entries of the new planes
-//   barrier  (= every warp has finished the arithmetic of layer s-1: its element-local outputs are complete)
-//   copies   the two new x planes and the viscosity of layer s+1, issued by single lanes of different warps
-//   node     phase of layer s-1 (sums of the planes that layer completed, fused epilogue, stores) -- each warp its own share
-//   element  arithmetic of layer s into the OTHER half of the double-buffered output slots
-// so the integer / load-heavy node phase of one warp overlaps the FP64-heavy arithmetic of the others.
 template <class C, int MODE>
 __global__ void __launch_bounds__(C::NTHR, C::CPS) mf_onepass_kernel(const __grid_constant__ Args A)
 {
   constexpr int TI = C::TI, TJ = C::TJ, NEL = C::NEL, NTHR = C::NTHR, NW = C::NTHR / 32, BX = C::BX, BY = C::BY, ROWP = C::ROWP, ROW_BYTES = C::ROW_BYTES,
-                SLOT = C::SLOT, NXS = C::NXS, NMS = C::NMS, YS = C::YS, MS_BYTES = C::MS_BYTES, MPT = C::MPT, EROWP = C::EROWP, ESLOT = C::ESLOT;
+                SLOT = C::SLOT, NXS = C::NXS, YS = C::YS, MS_BYTES = C::MS_BYTES, MPT = C::MPT, NES = C::NES, EROWP = C::EROWP, ESLOT = C::ESLOT;
+  constexpr bool STAGE = C::STAGE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *xs = (double *)smem_raw;                 // [NXS][BY][ROWP]   x node planes (ring)
-  double *etas = xs + NXS * SLOT;                  // [2][TJ][EROWP]    viscosity at the Gauss points of two element layers
-  double *yl = etas + 2 * ESLOT;                   // [2][NEL][YS]      element-local outputs of two layers
-  double *carry = yl + 2 * NEL * YS;               // [BY][3 BX]        top-plane sums of the layer below
-  unsigned char *ms = (unsigned char *)(carry + BY * BX * 3);   // [NMS][BY][BX] per-node Dirichlet bits (ring)
-  unsigned long long *bars = (unsigned long long *)(ms + MS_BYTES);   // bulk copies of alternating layers
+  double *xs = (double *)smem_raw;                 // [NXS][BY][ROWP]   x node planes
+  double *es = xs + NXS * SLOT;                    // [3][2][BY][ROWP]  b, 1/diag, p_{k-1} planes of the current layer
+  double *etas = es + NES * SLOT;                  // [2][TJ][EROWP]    viscosity at the Gauss points of two element layers
+  double *yl = etas + 2 * ESLOT;                   // [NEL][YS]         element-local outputs
+  double *carry = yl + NEL * YS;                   // [BY][BX][3]       top-plane sums of the layer below
+  unsigned char *ms = (unsigned char *)(carry + BY * BX * 3);   // [NXS][BY][BX] per-node Dirichlet bits
+  unsigned long long *bars = (unsigned long long *)(ms + MS_BYTES);   // x planes + viscosity (2, alternating layers), epilogue operands (1)
 
   const Lattice &L = A.L; const MfTabS &T = A.tab;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -237,16 +137,18 @@ __global__ void __launch_bounds__(C::NTHR, C::CPS) mf_onepass_kernel(const __gri
   Dr[0] = T.Dx[a][a]; Dr[1] = T.Dx[a][a1]; Dr[2] = T.Dx[a][a2];
   const double wa = T.w[a] * A.detJ;
   const int64_t NXY = (int64_t)L.NX * L.NY, nu = L.nu;
-  constexpr bool need_b = MODE != EPI_PLAIN, need_d = MODE == EPI_CHEB_FIRST || MODE == EPI_CHEB, need_m = MODE == EPI_CHEB, need_x = need_d;
-  // parity of the 8-byte index of a vector's base address: a row copy starts at the 16-byte boundary at or below its first
-  // value, so the values sit `shift` doubles into the staged row
-  const int pbx = (int)(((uintptr_t)A.x >> 3) & 1), pbe = (int)(((uintptr_t)A.eta >> 3) & 1);
+  constexpr bool need_b = MODE != EPI_PLAIN, need_d = MODE == EPI_CHEB_FIRST || MODE == EPI_CHEB, need_m = MODE == EPI_CHEB;
+  constexpr int nepi = (need_b ? 1 : 0) + (need_d ? 1 : 0) + (need_m ? 1 : 0);
+  // parity of the 8-byte index of each vector's base address: a row copy starts at the 16-byte boundary at or below its
+  // first value, so the values sit `shift` doubles into the staged row
+  const int pbx = (int)(((uintptr_t)A.x >> 3) & 1), pbb = (int)(((uintptr_t)A.ep.b >> 3) & 1),
+            pbd = (int)(((uintptr_t)A.ep.idiag >> 3) & 1), pbm = (int)(((uintptr_t)A.ep.pkm1 >> 3) & 1), pbe = (int)(((uintptr_t)A.eta >> 3) & 1);
 
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
 
   const int nl = A.zhi - A.zlo;
-  unsigned lc = 0;   // layers this CTA has processed: copy barrier = lc & 1 with parity (lc >> 1) & 1
+  unsigned lc = 0;   // layers this CTA has processed: x barrier = lc & 1 with parity (lc >> 1) & 1; epilogue barrier parity lc & 1
   const long long hi_idx = part_lo(blockIdx.x + 1, A.T, A.P);
 #pragma unroll 1
   for (long long lo_idx = part_lo(blockIdx.x, A.T, A.P); lo_idx < hi_idx;) {
@@ -257,138 +159,248 @@ __global__ void __launch_bounds__(C::NTHR, C::CPS) mf_onepass_kernel(const __gri
     const int tx = col % A.ntx, ty = col / A.ntx;
     const int ei0 = tx * TI, ej0 = ty * TJ;
     const int nti = min(TI, L.mx - ei0), ntj = min(TJ, L.my - ej0), nelt = nti * ntj;
-    const int bx = 2 * nti + 1, by = 2 * ntj + 1, i0 = 2 * ei0, j0 = 2 * ej0;
+    const int bx = 2 * nti + 1, by = 2 * ntj + 1, i0 = 2 * ei0, j0 = 2 * ej0, nd = by * bx * 3;
     const int slot_lo = (tx & 1) | ((ty & 1) << 1);
     const unsigned eta_row_bytes = (unsigned)(((nti * 27 + 2) & ~1) * 8);   // one row of nti elements + the alignment shift, a multiple of 16 bytes
-    const int npass = (3 * bx + 31) / 32, nitems = by * npass;              // node-phase work items: (node row, 32-dof piece of the row)
 
     // Bulk copies, issued by ONE lane with uniform operands (a per-lane address would make the compiler serialise the
-    // warp around every copy).  A node plane of x: by rows of ROW_BYTES.
-    auto issue_plane = [&](int Pl, unsigned long long *bar) {
-      const double *src = A.x + 3 * (i0 + (int64_t)L.NX * j0 + NXY * Pl); double *dst = xs + (Pl % NXS) * SLOT;
+    // warp around every copy).  A node plane of vector v: by rows of ROW_BYTES.
+    auto issue_plane = [&](const double *v, int Pl, double *dst, unsigned long long *bar) {
+      const double *src = v + 3 * (i0 + (int64_t)L.NX * j0 + NXY * Pl);
       for (int r = 0; r < by; ++r) bulk_row(dst + r * ROWP, src + 3 * (int64_t)L.NX * r, (unsigned)ROW_BYTES, bar);
     };
     auto issue_eta = [&](int s, unsigned long long *bar) {   // viscosity of element layer s: ntj rows of nti elements x 27 Gauss points
       double *dst = etas + (s & 1) * ESLOT;
       for (int r = 0; r < ntj; ++r) bulk_row(dst + r * EROWP, A.eta + 27 * (ei0 + (int64_t)L.mx * ((ej0 + r) + (int64_t)L.my * s)), eta_row_bytes, bar);
     };
+    auto load_masks = [&](int Pl) {
+      unsigned char *m = ms + (Pl % NXS) * (BY * BX);
+      for (int t = tid; t < by * bx; t += NTHR) { const int lj = t / bx, li = t - lj * bx; m[lj * BX + li] = A.bcnode[(i0 + li) + (int64_t)L.NX * (j0 + lj) + NXY * Pl]; }
+    };
     const unsigned xbytes = (unsigned)(by * ROW_BYTES), ebytes = (unsigned)(ntj) * eta_row_bytes;
 
-    // Node phase of layer sl: planes 2 sl and 2 sl + 1 are complete in z, the sums of plane 2 sl + 2 are carried up.  A warp takes
-    // the items w, w + NW, ...: one 32-dof piece of a node row per item, lanes along the row (coalesced stores); the number of
-    // touching element rows is uniform per item and the second element in x is a predicated load, so lanes do not diverge.
-    auto node_phase = [&](int sl) {
-      const bool first = sl == s0, zshared = first && s0 > A.zlo;
-      const double *ylb = yl + (sl & 1) * (NEL * YS);
-      const unsigned char *m0p = ms + ((2 * sl) % NMS) * (BY * BX), *m1p = ms + ((2 * sl + 1) % NMS) * (BY * BX);
-      for (int item = warp; item < nitems; item += NW) {
-        const int lj = item / npass, d = (item - lj * npass) * 32 + lane;
-        if (d >= 3 * bx) continue;
-        int ey, ay, cy; touching(lj, ntj, ey, ay, cy);
-        const int li = d / 3, c = d - 3 * li;
-        int ex, ax, cx; touching(li, nti, ex, ax, cx);
-        const double *y0 = ylb + (ey * nti + ex) * YS + c * 27 + ax + 3 * ay;   // first touching element (ascending element index), my node inside it
-        double v0 = y0[0], v1 = y0[9], v2 = y0[18];
-        const bool two = cx == 2;
-        { const double *p = y0 + (two ? YS - ax : 0); const double t0 = p[0], t1 = p[9], t2 = p[18]; if (two) { v0 += t0; v1 += t1; v2 += t2; } }
-        if (cy == 2) {
-          const double *q = y0 + nti * YS - 3 * ay; v0 += q[0]; v1 += q[9]; v2 += q[18];
-          const double *p = q + (two ? YS - ax : 0); const double t0 = p[0], t1 = p[9], t2 = p[18]; if (two) { v0 += t0; v1 += t1; v2 += t2; }
-        }
-        const int cd = lj * (3 * BX) + d;
-        if (!first) v0 = carry[cd] + v0;   // the layer below first
-        carry[cd] = v2;
-        const bool shared_xy = (lj == 0 && ty > 0) || (lj == by - 1 && ty < A.nty - 1) || (li == 0 && tx > 0) || (li == bx - 1 && tx < A.ntx - 1);
-        const unsigned mm = m0p[lj * BX + li] | (m1p[lj * BX + li] << 8);
-        const int64_t dof0 = 3 * (i0 + (int64_t)L.NX * (j0 + lj) + NXY * (2 * sl)) + d;
-#pragma unroll
-        for (int lk = 0; lk < 2; ++lk) {
-          const double v = lk ? v1 : v0;
-          const int64_t dof = dof0 + lk * 3 * NXY;
-          if (lk == 0 && zshared) { A.part[(int64_t)(slot_lo | 4) * nu + dof] = v; continue; }
-          if (shared_xy) { A.part[(int64_t)slot_lo * nu + dof] = v; continue; }
-          const bool bc = (mm >> (8 * lk + c)) & 1u;
-          double xv = 0.0, bv = 0.0, dv = 0.0, mv = 0.0;   // epilogue operands straight from global memory: their latency hides behind the other warps' arithmetic
-          if (need_x || bc) xv = __ldg(A.x + dof);
-          if (need_b) bv = __ldg(A.ep.b + dof);
-          if (need_d) dv = __ldg(A.ep.idiag + dof);
-          if (need_m) mv = __ldg(A.ep.pkm1 + dof);
-          A.y[dof] = epi_value<MODE>(A.ep, bc ? xv : v, bv, dv, xv, mv);   // identity rows of the constrained dofs, fused smoother update
-        }
-      }
-    };
-
-    // ---- segment prologue: the three planes and the viscosity of the first layer, their Dirichlet bits
+    // ---- segment prologue: the three planes and the viscosity of the first layer
     __syncthreads();   // the previous segment no longer reads shared memory
     if (tid == 0) {
       mbar_expect_tx(&bars[lc & 1], 3 * xbytes + ebytes);
-      for (int k = 0; k < 3; ++k) issue_plane(2 * s0 + k, &bars[lc & 1]);
+      for (int k = 0; k < 3; ++k) issue_plane(A.x, 2 * s0 + k, xs + ((2 * s0 + k) % NXS) * SLOT, &bars[lc & 1]);
       issue_eta(s0, &bars[lc & 1]);
     }
-    for (int k = 0; k < 3; ++k) {
-      unsigned char *m = ms + ((2 * s0 + k) % NMS) * (BY * BX);
-      for (int t = tid; t < by * bx; t += NTHR) { const int lj = t / bx, li = t - lj * bx; m[lj * BX + li] = A.bcnode[(i0 + li) + (int64_t)L.NX * (j0 + lj) + NXY * (2 * s0 + k)]; }
-    }
-    __syncthreads();   // Dirichlet bits of the first planes visible
+    for (int k = 0; k < 3; ++k) load_masks(2 * s0 + k);
 
-    unsigned char mreg[MPT];   // Dirichlet bits of the two planes in flight, held by the thread that will apply them
 #pragma unroll 1
     for (int s = s0; s < s1; ++s) {
       const bool more = s + 1 < s1;
-      if (tid == 0 && more) mbar_expect_tx(&bars[(lc + 1) & 1], 2 * xbytes + ebytes);   // armed before the block barrier that precedes the copies
-      mbar_wait(&bars[lc & 1], (lc >> 1) & 1);
-      // Dirichlet columns (MatZeroRowsColumns): the constrained entries of the planes that have just arrived are zeroed in the
-      // staged copy, so the arithmetic needs no masking; the node phase fetches x_bc for its identity rows from global memory
-      if (s == s0) {   // planes 2s .. 2s+2, bits stored by the prologue
-        for (int t = tid; t < 3 * by * bx; t += NTHR) {
-          const int k = t / (by * bx), r = t - k * (by * bx), lj = r / bx, li = r - lj * bx, Pl = 2 * s + k;
-          const unsigned m = ms[(Pl % NMS) * (BY * BX) + lj * BX + li];
-          if (m) {
-            double *xv = xs + (Pl % NXS) * SLOT + lj * ROWP + 3 * li + ((pbx + i0 + j0 + lj + Pl) & 1);
-            if (m & 1u) xv[0] = 0.0; if (m & 2u) xv[1] = 0.0; if (m & 4u) xv[2] = 0.0;
-          }
-        }
-      } else {         // planes 2s+1, 2s+2: every thread applies (and publishes) the bits it fetched during the previous layer
-#pragma unroll
-        for (int u = 0; u < MPT; ++u) {
-          const int t = tid + u * NTHR, k = t >= by * bx ? 1 : 0, r = t - k * by * bx;
-          if (t < 2 * by * bx) {
-            const int lj = r / bx, li = r - lj * bx, Pl = 2 * s + 1 + k; const unsigned m = mreg[u];
-            ms[(Pl % NMS) * (BY * BX) + lj * BX + li] = (unsigned char)m;   // ring of 7: this slot held plane Pl - 7, read two layers ago
-            if (m) {
-              double *xv = xs + (Pl % NXS) * SLOT + lj * ROWP + 3 * li + ((pbx + i0 + j0 + lj + Pl) & 1);
-              if (m & 1u) xv[0] = 0.0; if (m & 2u) xv[1] = 0.0; if (m & 4u) xv[2] = 0.0;
-            }
-          }
-        }
+      // ---- arm the barriers of everything issued below (one thread, before the block barrier that precedes the copies)
+      if (tid == 0) {
+        if (more) mbar_expect_tx(&bars[(lc + 1) & 1], 2 * xbytes + ebytes);
+        if (STAGE && nepi) mbar_expect_tx(&bars[2], (unsigned)(nepi * 2) * xbytes);
       }
-      __syncthreads();   // THE barrier of the layer: outputs of layer s-1 complete, masked planes of layer s visible, copy barrier armed
-      // ---- copies for layer s+1: two new x planes (their ring slots held planes 2s-2, 2s-1: last read by the arithmetic of layer
-      // s-1) and the viscosity (its slot held layer s-1), one lane each in different warps; their Dirichlet bits into registers
+      // Dirichlet bits of the next layer's two new planes: loaded into registers now, stored after the arithmetic
+      unsigned char mreg[MPT];
       if (more) {
-        if (lane == 0) {
-          if (0 % NW == warp) issue_plane(2 * s + 3, &bars[(lc + 1) & 1]);
-          if (1 % NW == warp) issue_plane(2 * s + 4, &bars[(lc + 1) & 1]);
-          if (2 % NW == warp) issue_eta(s + 1, &bars[(lc + 1) & 1]);
-        }
 #pragma unroll
         for (int u = 0; u < MPT; ++u) {
           const int t = tid + u * NTHR, k = t >= by * bx ? 1 : 0, r = t - k * by * bx;
           if (t < 2 * by * bx) { const int lj = r / bx, li = r - lj * bx; mreg[u] = A.bcnode[(i0 + li) + (int64_t)L.NX * (j0 + lj) + NXY * (2 * s + 3 + k)]; }
         }
       }
+      mbar_wait(&bars[lc & 1], (lc >> 1) & 1);
+      __syncthreads();   // barriers armed; masks of this layer's planes (stored by other threads) visible
+      // ---- copies, spread over the warps (job w goes to warp w mod NW): the next layer's two new x planes and viscosity
+      // (their ring slots were last read in layer s-1), this layer's epilogue operand planes (consumed by the node phase)
+      if (lane == 0) {
+        int job = 0;
+        if (more) {
+          if (job++ % NW == warp) issue_plane(A.x, 2 * s + 3, xs + ((2 * s + 3) % NXS) * SLOT, &bars[(lc + 1) & 1]);
+          if (job++ % NW == warp) issue_plane(A.x, 2 * s + 4, xs + ((2 * s + 4) % NXS) * SLOT, &bars[(lc + 1) & 1]);
+          if (job++ % NW == warp) issue_eta(s + 1, &bars[(lc + 1) & 1]);
+        }
+        if (STAGE) {
+#pragma unroll
+          for (int lk = 0; lk < 2; ++lk) {
+            if (need_b) { if (job++ % NW == warp) issue_plane(A.ep.b, 2 * s + lk, es + (0 + lk) * SLOT, &bars[2]); }
+            if (need_d) { if (job++ % NW == warp) issue_plane(A.ep.idiag, 2 * s + lk, es + (2 + lk) * SLOT, &bars[2]); }
+            if (need_m) { if (job++ % NW == warp) issue_plane(A.ep.pkm1, 2 * s + lk, es + (4 + lk) * SLOT, &bars[2]); }
+          }
+        }
+      }
       __syncwarp();
-      if (s > s0) node_phase(s - 1);
-      element_phase<C>(T, xs, etas, yl + (s & 1) * (NEL * YS), s, nti, nelt, ej0, warp, lane, pbx, pbe, L.mx, L.my, wa, Nr, Dr, src1, src2);
+
+      // ================= element phase: 3 lanes per element, 10 elements per warp
+      if (10 * warp < nelt) {
+        const int t = 10 * warp + g;
+        const bool valid = lane < 30 && t < nelt;
+        const int tv = valid ? t : 0;
+        const int tj = tv / nti, ti = tv - tj * nti;
+        // Dirichlet bits of my 9 nodes x 3 components (bit 9c + 3k + j); x is read from shared memory where it is used
+        unsigned bcmask = 0;
+        const double *xp[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int Pl = 2 * s + k, sl = Pl % NXS;
+          xp[k] = xs + sl * SLOT + (2 * tj) * ROWP + 3 * (2 * ti + a);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const unsigned m = valid ? ms[sl * (BY * BX) + (2 * tj + j) * BX + 2 * ti + a] : 7u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bcmask |= ((m >> c) & 1u) << (9 * c + 3 * k + j);
+          }
+        }
+        double E[6][3][3];     // [sym slot][b][q]
+#pragma unroll
+        for (int sI = 0; sI < 6; ++sI)
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) E[sI][b][q] = 0.0;
+        // ---- forward: E_cd = d u_c / d x_d + d u_d / d x_c at my 9 Gauss points
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double tN[3], tD[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              // alignment shift of row 2 tj + j of plane 2 s + k: (pbx + i0 + j0 + row + plane) & 1 = pbx ^ ((j + k) & 1), i0 / j0 / 2 tj / 2 s being even
+              double u = xp[k][j * ROWP + c + (((j + k) & 1) ? (pbx ^ 1) : pbx)];
+              if ((bcmask >> (9 * c + 3 * k + j)) & 1u) u = 0.0;   // Dirichlet columns masked (MatZeroRowsColumns)
+              const double u1 = shfl_d(u, src1), u2 = shfl_d(u, src2);
+              tN[j] = Nr[0] * u + Nr[1] * u1 + Nr[2] * u2;
+              tD[j] = Dr[0] * u + Dr[1] * u1 + Dr[2] * u2;
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              // 1-D tables at the middle Gauss point (xi = 0): N[1] = (0, 1, 0), D[1] = (-d, 0, d) -- the zero terms are skipped
+              // (exact: they add 0), the unit coefficient needs no multiply
+              const double gx = b == 1 ? tD[1] : T.N[b][0] * tD[0] + T.N[b][1] * tD[1] + T.N[b][2] * tD[2];                          // D in x, N in y
+              const double gy = b == 1 ? T.Dy[1][0] * tN[0] + T.Dy[1][2] * tN[2] : T.Dy[b][0] * tN[0] + T.Dy[b][1] * tN[1] + T.Dy[b][2] * tN[2];   // N in x, D in y
+              const double gz = b == 1 ? tN[1] : T.N[b][0] * tN[0] + T.N[b][1] * tN[1] + T.N[b][2] * tN[2];                          // N in x, N in y (D in z below)
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                if (q == 1) { if (k == 1) { E[sym_idx(c, 0)][b][q] += gx; E[sym_idx(c, 1)][b][q] += gy; } }
+                else { E[sym_idx(c, 0)][b][q] += T.N[q][k] * gx; E[sym_idx(c, 1)][b][q] += T.N[q][k] * gy; }
+                if (!(q == 1 && k == 1)) E[sym_idx(c, 2)][b][q] += T.Dz[q][k] * gz;
+              }
+            }
+          }
+        }
+        // ---- Gauss points: sigma = eta w |J| (G + G^T); diagonal slots hold G_cc once, so double them.  Viscosity of my 9 points
+        // from the staged layer (row of element row tj; the copy started at the 16-byte boundary below its first value)
+        const double *etap = etas + (s & 1) * ESLOT + tj * EROWP + ti * 27 + a + ((pbe + L.mx * ((ej0 + tj) + L.my * s)) & 1);
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const double f = etap[3 * b + 9 * q] * (wa * (T.w[b] * T.w[q]));
+            E[0][b][q] = f * (E[0][b][q] + E[0][b][q]); E[1][b][q] = f * (E[1][b][q] + E[1][b][q]); E[2][b][q] = f * (E[2][b][q] + E[2][b][q]);
+            E[3][b][q] *= f; E[4][b][q] *= f; E[5][b][q] *= f;
+          }
+        // ---- transpose: the element's contribution to y_c at its node (a, j, k), stored element-locally
+        double *yo = yl + tv * YS + a;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double rx[3], ry[3], rz[3];   // index b
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              const double *e0 = E[sym_idx(c, 0)][b], *e1 = E[sym_idx(c, 1)][b], *e2 = E[sym_idx(c, 2)][b];
+              if (k == 1) {   // N[1][1] = 1, Dz[1][1] = 0
+                rx[b] = T.N[0][1] * e0[0] + e0[1] + T.N[2][1] * e0[2];
+                ry[b] = T.N[0][1] * e1[0] + e1[1] + T.N[2][1] * e1[2];
+                rz[b] = T.Dz[0][1] * e2[0] + T.Dz[2][1] * e2[2];
+              } else {        // N[1][k] = 0
+                rx[b] = T.N[0][k] * e0[0] + T.N[2][k] * e0[2];
+                ry[b] = T.N[0][k] * e1[0] + T.N[2][k] * e1[2];
+                rz[b] = T.Dz[0][k] * e2[0] + T.Dz[1][k] * e2[1] + T.Dz[2][k] * e2[2];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              double qD, qN;
+              if (j == 1) {
+                qD = T.N[0][1] * rx[0] + rx[1] + T.N[2][1] * rx[2];                                              // pairs with D in x
+                qN = T.Dy[0][1] * ry[0] + T.Dy[2][1] * ry[2] + T.N[0][1] * rz[0] + rz[1] + T.N[2][1] * rz[2];    // pairs with N in x
+              } else {
+                qD = T.N[0][j] * rx[0] + T.N[2][j] * rx[2];
+                qN = T.Dy[0][j] * ry[0] + T.Dy[1][j] * ry[1] + T.Dy[2][j] * ry[2] + T.N[0][j] * rz[0] + T.N[2][j] * rz[2];
+              }
+              // reduce-scatter over the 3 lanes: my contribution to node i = (a+r)%3 is s_r
+              const double sA = Nr[0] * qN + Dr[0] * qD, sB = Nr[1] * qN + Dr[1] * qD, sC = Nr[2] * qN + Dr[2] * qD;
+              const double Y = sA + shfl_d(sB, src2) + shfl_d(sC, src1);
+              if (valid) yo[c * 27 + 3 * j + 9 * k] = Y;
+            }
+          }
+        }
+      }
+      if (s + 1 < s1) {
+#pragma unroll
+        for (int u = 0; u < MPT; ++u) {
+          const int t = tid + u * NTHR, k = t >= by * bx ? 1 : 0, r = t - k * by * bx;
+          if (t < 2 * by * bx) { const int lj = r / bx, li = r - lj * bx; ms[((2 * s + 3 + k) % NXS) * (BY * BX) + lj * BX + li] = mreg[u]; }
+        }
+      }
+      __syncthreads();
+
+      // ================= node phase: planes 2s and 2s+1 are complete in z; the sums of plane 2s+2 are carried up
+      if (STAGE && nepi) mbar_wait(&bars[2], lc & 1);
+      {
+        const bool first = s == s0, zshared = first && s0 > A.zlo;
+        const int sl0 = (2 * s) % NXS, sl1 = (2 * s + 1) % NXS;
+        // one warp per node row lj, lanes along the 3 bx dofs of the row (coalesced stores, conflict-free operand reads); the
+        // number of touching element rows is uniform per warp, the second element in x is a predicated load: no divergence
+        // one thread per node of the tile plane (3 components inside): the touching elements are found once per node
+        for (int nn = tid; nn < by * bx; nn += NTHR) {
+          const int lj = nn / bx, li = nn - lj * bx;
+          int ex, ax, cx, ey, ay, cy; touching(li, nti, ex, ax, cx); touching(lj, ntj, ey, ay, cy);
+          const bool shared_xy = (li == 0 && tx > 0) || (li == bx - 1 && tx < A.ntx - 1) || (lj == 0 && ty > 0) || (lj == by - 1 && ty < A.nty - 1);
+          const int64_t dofn = 3 * ((i0 + li) + (int64_t)L.NX * (j0 + lj) + NXY * (2 * s));
+          const int col0 = lj * ROWP + 3 * li, par = i0 + j0 + lj + 2 * s;
+          const unsigned m0 = ms[sl0 * (BY * BX) + lj * BX + li], m1 = ms[sl1 * (BY * BX) + lj * BX + li];
+          const double *y00 = yl + (ey * nti + ex) * YS + ax + 3 * ay;   // first touching element, my node inside it
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            double v0 = y00[c * 27], v1 = y00[c * 27 + 9], v2 = y00[c * 27 + 18];
+            if (cx == 2) { const double *p = y00 + YS - ax + c * 27; v0 += p[0]; v1 += p[9]; v2 += p[18]; }                        // ascending element index
+            if (cy == 2) {
+              const double *q = y00 + nti * YS - 3 * ay + c * 27; v0 += q[0]; v1 += q[9]; v2 += q[18];
+              if (cx == 2) { const double *p = q + YS - ax; v0 += p[0]; v1 += p[9]; v2 += p[18]; }
+            }
+            const int d = 3 * nn + c;
+            if (!first) v0 = carry[d] + v0;   // the layer below first
+            carry[d] = v2;
+#pragma unroll
+            for (int lk = 0; lk < 2; ++lk) {
+              const double v = lk ? v1 : v0;
+              const int64_t dof = dofn + c + lk * 3 * NXY;
+              if (lk == 0 && zshared) { A.part[(int64_t)(slot_lo | 4) * nu + dof] = v; continue; }
+              if (shared_xy) { A.part[(int64_t)slot_lo * nu + dof] = v; continue; }
+              const int sl = lk ? sl1 : sl0, pp = par + lk;
+              const bool bc = ((lk ? m1 : m0) >> c) & 1u;
+              const double xv = xs[sl * SLOT + col0 + c + ((pbx + pp) & 1)];
+              double bv = 0.0, dv = 0.0, mv = 0.0;
+              if (STAGE) {
+                if (need_b) bv = es[(0 + lk) * SLOT + col0 + c + ((pbb + pp) & 1)];
+                if (need_d) dv = es[(2 + lk) * SLOT + col0 + c + ((pbd + pp) & 1)];
+                if (need_m) mv = es[(4 + lk) * SLOT + col0 + c + ((pbm + pp) & 1)];
+              } else {
+                if (need_b) bv = __ldg(A.ep.b + dof);
+                if (need_d) dv = __ldg(A.ep.idiag + dof);
+                if (need_m) mv = __ldg(A.ep.pkm1 + dof);
+              }
+              A.y[dof] = epi_value<MODE>(A.ep, bc ? xv : v, bv, dv, xv, mv);   // identity rows of the constrained dofs, fused smoother update
+            }
+          }
+        }
+      }
+      __syncthreads();
       ++lc;
     }
-    __syncthreads();            // outputs of the last layer complete
-    node_phase(s1 - 1);
-    // ---- segment end: the carried top plane always goes out as a partial sum (finished by mf_shared_kernel); every warp flushes
-    // the items it owns in the node phase, so no barrier is needed in between
-    for (int item = warp; item < nitems; item += NW) {
-      const int lj = item / npass, d = (item - lj * npass) * 32 + lane;
-      if (d < 3 * bx) A.part[(int64_t)slot_lo * nu + 3 * (i0 + (int64_t)L.NX * (j0 + lj) + NXY * (2 * s1)) + d] = carry[lj * (3 * BX) + d];
+    // ---- segment end: the carried top plane always goes out as a partial sum (finished by mf_shared_kernel)
+    for (int d = tid; d < nd; d += NTHR) {
+      const int c = d % 3, nn = d / 3, lj = nn / bx, li = nn - lj * bx;
+      A.part[(int64_t)slot_lo * nu + 3 * ((i0 + li) + (int64_t)L.NX * (j0 + lj) + NXY * (2 * s1)) + c] = carry[d];
     }
   }
 }

@@ -529,7 +529,9 @@ def test_abf_opts_verbatim_matches_oracle_fixture(mx):
         m = min(len(inner), len(inner_o))
         assert sum(abs(a - b) for a, b in zip(inner[:m], inner_o[:m])) <= 1
         F = g.rhs()
-        assert np.linalg.norm(F - g.mat_mult(X.MAT_A, x)) <= 3e-8 * np.linalg.norm(F)
+        # the true residual tracks the oracle's: at 32^3 the solve ends at iteration 30, just before the first restart would
+        # re-compute it, and one-pass classical Gram-Schmidt has let the estimate run ahead of it (oracle: 1.55e-7)
+        assert np.linalg.norm(F - g.mat_mult(X.MAT_A, x)) <= (1.5 * fx["true_rel_res"] + 1e-8) * np.linalg.norm(F)
         g.close()
 
 
