@@ -45,7 +45,7 @@ def workload_options(a):
 
 
 # measured once per kernel change with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/
-NCU_TRAFFIC = {("spmv_baij", 64, 1): 10.81e9, ("mf_onepass", 64, 1): 370.0e6}   # mf_onepass: Chebyshev-step launch, profiles/r02_onepass_cheb_t1_raw.csv (314 MB read + 56 MB written)
+NCU_TRAFFIC = {("spmv_baij", 64, 1): 10.81e9, ("mf_onepass", 64, 1): 354.9e6}   # mf_onepass: Chebyshev-step launch, profiles/r02_mf_onepass_64cubed_chebstep_raw.csv (305.8 MB read + 49.1 MB written)
 FP64_PEAK_TFLOPS = 36.72      # scripts/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak.json): 63.1 DFMA/clk/SM at 1965 MHz
 MF_FLOP_PER_ELEMENT = 5808.0  # FP64 flops the one-pass element kernel executes per element: 3 lanes x (723 DFMA x 2 + 376 DMUL + 114 DADD), cuobjdump -sass (zero / unit table entries skipped)
 

@@ -152,7 +152,7 @@ struct SolverOpts {
   int p_pc = 0;          // 0 ilu0 (bjacobi) 1 jacobi
   int time_kernels = 0;
   int mf_tile = 0;       // -xsb_mf_tile: tile variant of the one-pass element kernel (0: 16 x 5 elements, one CTA per SM; 1: 8 x 5, two CTAs per SM)
-  int mf_kernel = 3;     // -xsb_mf_kernel: 1 = 9 lanes per element, 2 / 3 = 3 lanes per element with preloaded / reduction scatter (xsb_mf.cu)
+  int mf_kernel = 4;     // -xsb_mf_kernel: 4 = one-pass TMA-staged kernel (xsb_mf1p.cu), 3 = 8-colour kernel (xsb_mf.cu)
   int mf_reverse = 1;    // -xsb_mf_reverse: successive colour launches sweep the mesh in alternating directions (L2 reuse)
   int mf_chunk = 0;      // -xsb_mf_chunk: element layers per z-chunk of the matrix-free apply (0 = sized for L2)
   int matrix_free = 0;   // -xsb_matrix_free: fine-level A00 products by the sum-factorised element kernel (xsb_mf.cu)

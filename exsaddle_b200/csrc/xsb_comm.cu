@@ -21,6 +21,7 @@ struct NcclApi {
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -37,7 +38,7 @@ static int nccl_load(xsb_ctx c)
   if (!g_nccl.h) return xsb_fail(c, XSB_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
 #define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) return xsb_fail(c, XSB_ERR_NCCL, "libnccl lacks %s", name)
   SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
-  SYM(AllReduce, "ncclAllReduce"); SYM(Broadcast, "ncclBroadcast"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+  SYM(AllReduce, "ncclAllReduce"); SYM(Broadcast, "ncclBroadcast"); SYM(AllGather, "ncclAllGather"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
   SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   return 0;
@@ -142,19 +143,14 @@ int comm_bcast_planes(xsb_ctx c, double *glob, int64_t pd, int nplanes_glob)
   return 0;
 }
 
-// Row-partitioned product on a replicated level: rank r holds fresh values for planes [r*n/N, (r+1)*n/N) of `glob`
+// Row-partitioned product on a replicated level: rank r holds fresh values for planes [r cp, (r+1) cp) of `glob`, cp = ceil(n / N)
+// (equal chunks: the vector is allocated with N cp planes, the tail beyond the lattice is padding), so the exchange is ONE
+// in-place ncclAllGather instead of N grouped broadcasts.
 int comm_allgather_planes(xsb_ctx c, double *glob, int64_t pd, int nplanes)
 {
   const Slab &S = c->slab;
   if (S.nranks == 1) return 0;
-  ncclComm_t comm = (ncclComm_t)c->nccl;
-  NCCL_OK(g_nccl.GroupStart());
-  for (int r = 0; r < S.nranks; ++r) {
-    const int64_t p0 = (int64_t)r * nplanes / S.nranks, p1 = (int64_t)(r + 1) * nplanes / S.nranks;
-    if (p1 <= p0) continue;
-    double *p = glob + p0 * pd;
-    NCCL_OK(g_nccl.Broadcast(p, p, (size_t)((p1 - p0) * pd), ncclFloat64_, r, comm, c->stream));
-  }
-  NCCL_OK(g_nccl.GroupEnd());
+  const int64_t cp = (nplanes + S.nranks - 1) / S.nranks;
+  NCCL_OK(g_nccl.AllGather(glob + (int64_t)S.rank * cp * pd, glob, (size_t)(cp * pd), ncclFloat64_, (ncclComm_t)c->nccl, c->stream));
   return 0;
 }

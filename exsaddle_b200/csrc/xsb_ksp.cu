@@ -60,6 +60,7 @@ int op_full_mult(xsb_ctx c, const double *x, double *y)
 {
   if (c->no_A) {   // operator-free: y_u = A00 x_u (element kernel) + A01 x_p ; y_p = A11 x_p + A10 x_u
     const Lattice &L = c->lat; Epilogue ep;
+    XSB_CHK(mf_setup(c));   // returns at once when the element-kernel state is current (the product may precede xsb_ksp_setup)
     XSB_CHK(comm_halo_full(c, const_cast<double *>(x)));
     XSB_CHK(mf_a00_apply(c, x, y, ep));
     XSB_CHK(spmv_csr(c, c->A01, x + L.nu, y, c->own_u.off0, c->own_u.len0, y));
@@ -138,7 +139,7 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reaso
 // ------------------------------------------------------------------ options -> solver tree (KSPSetFromOptions)
 static int read_solver_options(xsb_ctx c)
 {
-  Options &o = c->opt; SolverOpts &s = c->so; s = SolverOpts();
+  Options &o = c->opt; SolverOpts &s = c->so; s = SolverOpts(); c->mf_opts_read = false;   // the element-kernel options live in `so` too
   const std::string ksp = o.str("saddle_ksp_type", "gmres");
   if (ksp == "gmres") s.ksp_type = 0; else if (ksp == "fgmres") s.ksp_type = 1;
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_ksp_type %s not supported (gmres|fgmres)", ksp.c_str());

@@ -635,20 +635,24 @@ int mg_setup(xsb_ctx c)
     else if (c->no_A && l == levels - 2) XSB_CHK(galerkin_elements(c, C));
     else XSB_CHK(galerkin(c, F, C));
   }
-  for (int l = 0; l < levels; ++l) {
-    Level &L = c->lev[l]; const int64_t n = (int64_t)L.A.nb * L.A.bs;
-    XSB_CHK(dev_alloc(c, &L.x, (size_t)n)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)n));
-    XSB_CHK(dev_alloc(c, &L.w0, (size_t)n)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)n)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
-    if (c->no_A && l == levels - 1) XSB_CHK(mf_diag_inv(c, L.idiag)); else XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
-  }
-  // large replicated levels: split the rows of every smoother / residual product over the ranks (-xsb_rowpart_min_nodes)
+  // large replicated levels: split the rows of every smoother / residual product over the ranks (-xsb_rowpart_min_nodes): rank r
+  // computes the planes [r cp, (r+1) cp), cp = ceil(nz / N), and ONE in-place all-gather of equal chunks replicates the result
+  // (the vectors such a product writes are allocated with N cp planes)
   if (dist) {
     const int64_t min_nodes = c->opt.integer("xsb_rowpart_min_nodes", 100000);
     for (int l = 1; l < levels - 1; ++l) {
       Level &L = c->lev[l];
       if ((int64_t)L.A.nb < min_nodes || L.nz < S.nranks) continue;
-      L.rowpart = true; L.rp0 = (int)((int64_t)S.rank * L.nz / S.nranks); L.rp1 = (int)((int64_t)(S.rank + 1) * L.nz / S.nranks);
+      const int cp = (L.nz + S.nranks - 1) / S.nranks;
+      L.rowpart = true; L.rp0 = S.rank * cp < L.nz ? S.rank * cp : L.nz; L.rp1 = (S.rank + 1) * cp < L.nz ? (S.rank + 1) * cp : L.nz;
     }
+  }
+  for (int l = 0; l < levels; ++l) {
+    Level &L = c->lev[l]; const int64_t n = (int64_t)L.A.nb * L.A.bs;
+    const int64_t npad = L.rowpart ? (int64_t)((L.nz + S.nranks - 1) / S.nranks) * S.nranks * L.nx * L.ny * L.A.bs : n;
+    XSB_CHK(dev_alloc(c, &L.x, (size_t)npad)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)npad));
+    XSB_CHK(dev_alloc(c, &L.w0, (size_t)npad)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)npad)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
+    if (c->no_A && l == levels - 1) XSB_CHK(mf_diag_inv(c, L.idiag)); else XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
   }
   XSB_CHK(coarse_setup(c));
   for (int l = 1; l < levels; ++l) {

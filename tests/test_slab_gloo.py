@@ -70,6 +70,18 @@ def _worker(rank, world, port, mx, my, mz, q):
         for z in range(zp0, zp1 + 1):
             zl = z - lay["e0"]
             assert np.array_equal(loc[nu_loc + zl * pp: nu_loc + (zl + 1) * pp], xg[nu_g + z * pp: nu_g + (z + 1) * pp]), ("p plane", z)
+        # 4. replay comm_allgather_planes (row-partitioned product on a replicated coarse level): nz planes, equal chunks of
+        #    cp = ceil(nz / N) planes, the vector padded to N cp planes, rank r fills [r cp, min((r+1) cp, nz))
+        for nz, pd in ((mz + 1, 7), (2 * mz + 1, 5)):
+            cp = -(-nz // world)
+            want = np.cos(0.11 * np.arange(nz * pd))
+            buf = np.full(world * cp * pd, -1.0)
+            r0, r1 = min(rank * cp, nz), min((rank + 1) * cp, nz)
+            buf[r0 * pd:r1 * pd] = want[r0 * pd:r1 * pd]
+            parts = [torch.empty(cp * pd, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(buf[rank * cp * pd:(rank + 1) * cp * pd].copy()))
+            got = torch.cat(parts).numpy()
+            assert np.array_equal(got[:nz * pd], want), ("all-gather of equal padded chunks", nz)
         dist.barrier(); dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception as e:   # report instead of hanging the parent
