@@ -290,7 +290,7 @@ def main():
                        "first Galerkin level assembled element by element, coarse levels BAIJ(3)",
                  False: "assembled: A in the reference's MATAIJ layout, A00 and Galerkin levels BAIJ(3)"}
     cfg = {"workload": workload_name(a), "path": path_text[headline_opfree], "unknowns": 3 * (2 * a.mx + 1) ** 3 + (a.mx + 1) ** 3, "mg_levels": a.levels,
-           "parallelism": "1 GPU" if world == 1 else "one problem, z-slab partition over %d GPUs (one process per GPU): NCCL send/recv halo exchange before every operator apply, NCCL all-reduce for Krylov dot products; fine MG level distributed, coarse levels replicated (products of the large ones row-partitioned + all-gathered), ILU(0) per rank (bjacobi)" % world,
+           "parallelism": "1 GPU" if world == 1 else "one problem, z-slab partition over %d GPUs (one process per GPU): ghost planes exchanged by one kernel over NVLink peer memory (cudaIpc windows, flag handshake; -xsb_p2p 0: ncclSend/ncclRecv) before every fine-level operator apply, NCCL all-reduce for Krylov dot products; fine MG level on the slab lattice, large coarse levels distributed by node planes (one plane of every product's result traded with each neighbour), small ones replicated, ILU(0) per rank (bjacobi)" % world,
            "l2": "x, y, viscosity and the Galerkin levels (>= 0.7 GB at 64^3; assembled path: A00 BAIJ 10.4 GB) exceed the 126 MB L2; no flush needed",
            "options": workload_options(a)}
 
@@ -358,7 +358,8 @@ def main():
         clocks = sampler.stop() if sampler else None
         its, reason = g.iterations(); inner = g.inner_iterations(); hist = g.history()
         parity = parity_check(g, X, torch, dist, b, world, xdev, its, reason, inner, [float(v) for v in hist])
-        out = {"outer_its": int(its), "reason": int(reason), "inner_gcr_its": int(sum(inner)), "rnorm0": float(hist[0]), "rnorm": float(hist[-1]),
+        ci = g.comm_info()
+        out = {"comm": {"peer_memory_halo": ci["p2p"], "plane_distributed_mg_levels": ci["pdist_levels"]}, "outer_its": int(its), "reason": int(reason), "inner_gcr_its": int(sum(inner)), "rnorm0": float(hist[0]), "rnorm": float(hist[-1]),
                "a00_products_per_solve": n_a00 // steps, "assemble_s": t_asm, "ksp_setup_s": t_setup, "gpu_launches": launches, "parity": parity, "clocks": clocks}
         ms_e2e = None
         if e2e:
@@ -394,6 +395,9 @@ def main():
             g.solve_dev(0, xdev.data_ptr()); barrier()
             ms_i, _, avg_ns, n_i, modes_i = timed_solves(g, torch, xdev, 1, barrier)
             share = (n_i * avg_ns * 1e-9) / (ms_i / 1e3)
+            # device time of that instrumented solve by category (graphs off, rank 0's view): where the step goes
+            out["profile"] = {"solve_ms": ms_i, "by_category_ms": {k: round(v[0], 3) for k, v in g.profile().items()}, "stretches": {k: int(v[1]) for k, v in g.profile().items()},
+                              "note": "one extra solve with -xsb_time_kernels (an event at every category change, CUDA graphs off), this rank's device time"}
             if opfree:
                 nel_apply = nel_local * own_frac if world > 1 else nel_local   # slabs: the kernel applies the layers touching owned planes
                 flops_alg = 9000.0 * nel_apply            # ~9.0 kflop per element, sum-factorised
@@ -433,9 +437,10 @@ def main():
     if a.mx == 64 and not a.no_strong128:
         import copy
         b = copy.copy(a); b.mx, b.levels = 128, 7
-        s128 = measure(b, True, 3, 1, e2e=False, instrument=False)
+        s128 = measure(b, True, 3, 1, e2e=False, instrument=True)
         strong = {"workload": workload_name(b), "path": "operator-free", "value": s128["value"], "unit": "s", "steps": 3, "warmup": 1, "outer_its": s128["outer_its"],
                   "inner_gcr_its": s128["inner_gcr_its"], "true_rel_residual": s128["parity"]["true_rel_residual"], "parity_ok": s128["parity"]["ok"],
+                  "profile": s128.get("profile"), "comm": s128.get("comm"), "element_kernel_avg_us": (s128.get("roofline") or {}).get("avg_launch_us"),
                   "note": "north-star strong-scaling workload (128^3, 7 MG levels): same value at every --gpus N, divide N = 1 by N x this for the efficiency"}
 
     if rank == 0:
@@ -464,7 +469,7 @@ def main():
                 "warmup": warmup, "ms_per_step": 1e3 * head["value"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
                 "solve": {k: head[k] for k in ("outer_its", "reason", "inner_gcr_its", "rnorm0", "rnorm", "a00_products_per_solve", "assemble_s", "ksp_setup_s")},
-                "parity": head["parity"], "roofline": head.get("roofline"),
+                "parity": head["parity"], "roofline": head.get("roofline"), "profile": head.get("profile"), "comm": head.get("comm"),
                 ("assembled" if headline_opfree else "operator_free"): None if other is None else {k: other.get(k) for k in ("value", "e2e", "outer_its", "inner_gcr_its", "gpu_launches", "parity", "roofline", "aij_matmult")},
                 "strong_128": strong, "cpu_baseline": base,
                 "e2e": {"value": head["e2e"], "unit": "s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n},

@@ -49,7 +49,7 @@ def lib():
             "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
             "xsb_ksp_setup": [vp], "xsb_ksp_reset": [vp], "xsb_get_state": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
             "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
-            "xsb_pc_schur_apply": [vp, dp, dp], "xsb_mg_restrict": [vp, C.c_int, dp, dp],
+            "xsb_pc_schur_apply": [vp, dp, dp], "xsb_time_pc_schur": [vp, C.c_int, dp], "xsb_mg_restrict": [vp, C.c_int, dp, dp],
             "xsb_mg_interpolate_add": [vp, C.c_int, dp, dp],
             "xsb_ksp_get_iterations": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "xsb_ksp_get_history": [vp, dp, C.c_int, C.POINTER(C.c_int)],
@@ -57,11 +57,13 @@ def lib():
             "xsb_ksp_get_inner_reasons": [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)],
             "xsb_ksp_get_chebyshev": [vp, C.c_int, dp, dp, dp, dp], "xsb_ksp_get_timing": [vp, dp, dp],
             "xsb_ksp_get_counters": [vp, i64p], "xsb_diagnostics": [vp, dp, dp], "xsb_get_stream": [vp, C.POINTER(vp)],
+            "xsb_ksp_get_profile": [vp, dp, i64p, C.c_int, C.POINTER(C.c_int)], "xsb_comm_info": [vp, i64p],
             "xsb_pattern_row": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, i32p, C.c_int],
             "xsb_prealloc_total": [C.c_int, C.c_int, C.c_int, C.c_int],
             "xsb_bc_list": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int],
             "xsb_mg_level_dims": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
             "xsb_slab_range": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+            "xsb_pdist_range": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "xsb_slab_layout": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64p],
             "xsb_comm_unique_id": [C.c_char_p], "xsb_comm_init": [vp, C.c_char_p, C.c_int, C.c_int], "xsb_get_partition": [vp, i64p],
         }
@@ -120,6 +122,15 @@ def slab_range(mz, nranks, rank):
     rc = lib().xsb_slab_range(mz, nranks, rank, C.byref(a), C.byref(b))
     if rc:
         raise XsbError(rc, "bad slab request")
+    return a.value, b.value
+
+
+def pdist_range(mz, nranks, rank, depth):
+    """Node planes of coarse MG level `depth` (0 = first coarse level) that `rank` computes (xsb_pdist_range)."""
+    a, b = C.c_int(), C.c_int()
+    rc = lib().xsb_pdist_range(mz, nranks, rank, depth, C.byref(a), C.byref(b))
+    if rc:
+        raise XsbError(rc, "bad plane-range request")
     return a.value, b.value
 
 
@@ -264,6 +275,10 @@ class ExSaddle:
         b = np.ascontiguousarray(b, dtype=np.float64); x = np.empty(self.nu)
         self._chk(self.L.xsb_pc_mg_apply(self.h, _dp(b), _dp(x))); return x
 
+    def time_pc_schur(self, reps=20):
+        ms = C.c_double()
+        self._chk(self.L.xsb_time_pc_schur(self.h, reps, C.byref(ms))); return ms.value
+
     def pc_schur_apply(self, b):
         b = np.ascontiguousarray(b, dtype=np.float64); x = np.empty(self.np_)
         self._chk(self.L.xsb_pc_schur_apply(self.h, _dp(b), _dp(x))); return x
@@ -331,6 +346,18 @@ class ExSaddle:
         self._chk(self.L.xsb_ksp_get_counters(self.h, out))
         return {"a00_spmv": out[0], "a_spmv": out[1], "launches": out[2], "a00_avg_ns": out[3],
                 "a00_by_mode": [out[4], out[5], out[6], out[7]]}
+
+    def profile(self):
+        """-xsb_time_kernels: {category: (ms, stretches)} of the last solve (xsb_ksp_get_profile)."""
+        ms = (C.c_double * 32)(); cnt = (C.c_int64 * 32)(); n = C.c_int()
+        self._chk(self.L.xsb_ksp_get_profile(self.h, ms, cnt, 32, C.byref(n)))
+        names = ["krylov_vectors_and_gaps", "fine_halo", "fine_a00"] + ["mg_level_%d" % l for l in range(10)] + ["coarse_plane_exchange", "transfers", "pressure_ilu", "full_operator", "fieldsplit_a01"]
+        return {names[i]: (ms[i], cnt[i]) for i in range(min(n.value, len(names))) if cnt[i]}
+
+    def comm_info(self):
+        out = (C.c_int64 * 4)()
+        self._chk(self.L.xsb_comm_info(self.h, out))
+        return {"rank": out[0], "nranks": out[1], "p2p": bool(out[2]), "pdist_levels": [l for l in range(16) if out[3] >> l & 1]}
 
     def stream(self):
         p = C.c_void_p()

@@ -121,7 +121,8 @@ struct Level {
   double emin = 0, emax = 0, emin_est = NAN, emax_est = NAN;
   double *x = nullptr, *b = nullptr, *r = nullptr, *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
   double *inv = nullptr;      // dense inverse of the coarsest operator
-  bool rowpart = false; int rp0 = 0, rp1 = 0;   // replicated level whose products are computed plane range [rp0,rp1) per rank, then all-gathered
+  bool pdist = false; int rp0 = 0, rp1 = 0;     // plane-distributed coarse level: vectors keep their GLOBAL indexing (and full length), but only the node planes [rp0-1, rp1+1) are kept current; this rank computes the rows of [rp0,rp1) and exchanges one plane with each neighbour
+  std::vector<int> cr0, cr1;                    // pdist level above a replicated one: the coarse planes each rank restricts
   bool dist = false;          // z-slab distributed level (vectors on the local lattice, ghost planes, owned-row products)
 };
 
@@ -158,6 +159,9 @@ struct SolverOpts {
   int matrix_free = 0;   // -xsb_matrix_free: fine-level A00 products by the sum-factorised element kernel (xsb_mf.cu)
 };
 
+// -xsb_time_kernels: categories the solve's time line is cut into (prof_mark, xsb_spmv.cu)
+enum { PROF_OTHER = 0, PROF_FINE_HALO, PROF_FINE, PROF_LVL, PROF_CHALO = PROF_LVL + XSB_MAX_LEVELS, PROF_XFER, PROF_ILU, PROF_FULL, PROF_CSR, PROF_N };
+
 struct xsb_ctx_s {
   int nsd = 3, lame = 0, device = 0;
   bool have_device = false;
@@ -188,6 +192,7 @@ struct xsb_ctx_s {
   double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr, *ilu_diag = nullptr; int ilu_nlvl = 0;
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;
+  bool ilup_on = false; double *ilup_packf = nullptr, *ilup_packb = nullptr; unsigned *ilup_prog = nullptr; double *ilup_y = nullptr; int ilup_dims[6] = {0, 0, 0, 0, 0, 0}; size_t ilup_smem = 0;   // line-pipelined ILU solve (xsb_ilu.cu)
   std::vector<double *> V, Z, GV, GS;   // outer Krylov basis, GCR bases
   double *w_t1 = nullptr, *w_t2 = nullptr, *gcr_r = nullptr, *fs_tu = nullptr, *xdev = nullptr, *bdev = nullptr, *mf_tmp = nullptr; unsigned char *mf_bcnode = nullptr, *mf_bczero = nullptr; bool mf_opts_read = false;
   double *mf_part = nullptr; int *mf_zitems = nullptr; int mf_nz = 0, mf_zkey[3] = {-1, -1, -1}, mf_sms = 0, mf_ready = 0;   // one-pass element kernel: partial sums of shared nodes, z-boundary list
@@ -199,9 +204,11 @@ struct xsb_ctx_s {
   float setup_ms = 0, solve_ms = 0;
   int64_t n_a00 = 0, n_a = 0, n_launch = 0, solve_launches = 0; double a00_ns_sum = 0; int64_t a00_timed = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
-  std::vector<cudaEvent_t> evpool; size_t ev_used = 0;   // event pairs around fine-level A00 launches (-xsb_time_kernels)
+  std::vector<cudaEvent_t> evpool; size_t ev_used = 0;   // -xsb_time_kernels: one event per mark, the stretch up to the next mark is booked on the mark's category
+  std::vector<int> ev_cat; double prof_ms[PROF_N] = {0}; int64_t prof_cnt[PROF_N] = {0};
   int64_t a00_mode[4] = {0, 0, 0, 0};                    // fine-level A00 launches per epilogue mode
   Slab slab; void *nccl = nullptr;          // ncclComm_t when nranks > 1
+  void *p2p = nullptr;                      // peer-memory halo windows (xsb_comm.cu), survives xsb_reset like the communicator
   Ranges own_full, own_u, own_p;            // owned entries of [u|p], u and p vectors on the local lattice
   std::vector<void *> allocs;   // every device allocation, for xsb_reset
   std::vector<char> alloc_phase; int phase = 0;   // 0: xsb_assemble, 1: xsb_ksp_setup (freed when the solver is set up again), 2: lazily created element-kernel state
@@ -232,6 +239,7 @@ int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0 =
 int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0 = 0, int nnodes = -1);
 int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);   // counted (+ timed) fine-level launch
 int spmv_collect_timing(xsb_ctx c);
+int prof_mark(xsb_ctx c, int cat);   // -xsb_time_kernels: the time from here to the next mark belongs to category `cat`
 // ---- xsb_mf.cu
 int mf_setup(xsb_ctx c);
 int mf_a00_apply(xsb_ctx c, const double *x, double *y, const Epilogue &ep);
@@ -270,7 +278,12 @@ int comm_halo_p(xsb_ctx c, double *p);            // pressure ghost planes (1 be
 int comm_halo_full(xsb_ctx c, double *x);         // [u|p]
 int comm_bcast_segments(xsb_ctx c, double *glob, const int64_t *offs /* nranks+1 */);
 int comm_bcast_planes(xsb_ctx c, double *glob, int64_t plane_doubles, int nplanes_glob);   // every rank contributes its owned coarse planes
-int comm_allgather_planes(xsb_ctx c, double *glob, int64_t plane_doubles, int nplanes);    // rank r contributes planes [r*n/N, (r+1)*n/N)
+int comm_bcast_plane_ranges(xsb_ctx c, double *glob, int64_t plane_doubles, const int *p0, const int *p1);   // rank r contributes planes [p0[r], p1[r])
+int comm_halo_planes(xsb_ctx c, double *v, int64_t plane_doubles, int o0, int o1, int gb, int ga);   // ghost planes of any lattice vector (owned planes [o0,o1))
+int comm_p2p_setup(xsb_ctx c);      // collective: peer-memory windows for the halo exchange (NVLink), called by xsb_assemble
+int comm_p2p_active(xsb_ctx c);
+int comm_p2p_check(xsb_ctx c);      // sticky time-out flag of the peer-memory exchange
+void comm_p2p_destroy(xsb_ctx c);
 inline Ranges whole(int64_t n) { Ranges r; r.len0 = n; return r; }
 // ---- xsb_mg.cu
 int mg_setup(xsb_ctx c);

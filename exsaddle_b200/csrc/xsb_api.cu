@@ -26,6 +26,7 @@ template int dev_alloc<int>(xsb_ctx, int **, size_t);
 template int dev_alloc<char>(xsb_ctx, char **, size_t);
 template int dev_alloc<unsigned char>(xsb_ctx, unsigned char **, size_t);
 template int dev_alloc<unsigned short>(xsb_ctx, unsigned short **, size_t);
+template int dev_alloc<unsigned>(xsb_ctx, unsigned **, size_t);
 
 int dev_free_all(xsb_ctx c)
 {
@@ -83,12 +84,12 @@ int xsb_reset(xsb_ctx c)
   if (!c) return XSB_ERR_ARG;
   if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); mg_graphs_release(c); mmg_free(c); fsd_free(c); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
   Options opt = c->opt; int nsd = c->nsd, lame = c->lame, device = c->device; bool hd = c->have_device;
-  const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl;
+  const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl, *p2p = c->p2p;
   cudaStream_t st = c->stream; cudaEvent_t e0 = c->ev0, e1 = c->ev1, k0 = c->evk0, k1 = c->evk1;
   *c = xsb_ctx_s();
   c->opt = opt; c->opt.used.clear(); c->nsd = nsd; c->lame = lame; c->device = device; c->have_device = hd;
   c->stream = st; c->ev0 = e0; c->ev1 = e1; c->evk0 = k0; c->evk1 = k1;
-  c->slab.rank = rank; c->slab.nranks = nranks; c->nccl = nccl;
+  c->slab.rank = rank; c->slab.nranks = nranks; c->nccl = nccl; c->p2p = p2p;
   return XSB_OK;
 }
 
@@ -171,6 +172,7 @@ int xsb_assemble(xsb_ctx c)
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   int rc = fe_assemble(c);
   if (rc) return rc;
+  XSB_CHK(comm_p2p_setup(c));   // slabs: peer-memory halo windows sized for this lattice (collective)
   CUDA_OK(cudaEventRecord(c->ev1, c->stream)); CUDA_OK(cudaEventSynchronize(c->ev1));
   return XSB_OK;
 }
@@ -378,6 +380,23 @@ int xsb_pc_schur_apply(xsb_ctx c, const double *b, double *x)
     return vec_pmult(cc, cc->lat.np, cc->mp_idiag, a, bb); });
 }
 
+// device time of `reps` pressure-block solves (ILU(0) or Jacobi) on resident vectors, CUDA events on the handle's stream
+int xsb_time_pc_schur(xsb_ctx c, int reps, double *ms_per_apply)
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready || c->so.pc_type != 2 || reps < 1 || !ms_per_apply) return xsb_fail(c, XSB_ERR_ORDER, "fieldsplit PC not set up");
+  double *a = c->w_t1, *bb = c->w_t2;
+  XSB_CHK(vec_set(c, c->lat.np, 1.0, a));
+  auto one = [&]() { return c->so.p_pc == 0 ? ilu_apply(c, a + c->own_p.off0, bb + c->own_p.off0) : vec_pmult(c, c->lat.np, c->mp_idiag, a, bb); };
+  XSB_CHK(one());
+  CUDA_OK(cudaEventRecord(c->evk0, c->stream));
+  for (int i = 0; i < reps; ++i) XSB_CHK(one());
+  CUDA_OK(cudaEventRecord(c->evk1, c->stream)); CUDA_OK(cudaEventSynchronize(c->evk1));
+  float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
+  *ms_per_apply = (double)ms / reps;
+  return XSB_OK;
+}
+
 int xsb_mg_restrict(xsb_ctx c, int lc, const double *rf, double *bc)
 {
   NEED_DEVICE(c);
@@ -462,7 +481,7 @@ int xsb_ksp_view(xsb_ctx c, char *buf, int buflen)
       if (l == 0 && c->nsub > 0) add("      level 0 (coarse): preonly + lu replaced by cg to 1e-13 preconditioned by an internal %d-level V-cycle (dense inverse at its bottom), rows=%lld, total: nonzeros=%lld, bs=%d; %d coarse solves, %d cg iterations so far\n", c->nsub, rows, nz, L.A.bs, c->coarse_solves, c->coarse_its);
       else if (l == 0) add("      level 0 (coarse): preonly + lu (dense inverse), rows=%lld, total: nonzeros=%lld, bs=%d\n", rows, nz, L.A.bs);
       else add("      level %d: chebyshev + jacobi, maximum iterations=%d, eigenvalue estimates used:  min = %g, max = %g%s, rows=%lld, total: nonzeros=%lld, bs=%d%s\n",
-               l, s.cheb_its, L.emin, L.emax, s.n_cheb_fixed ? " (set explicitly)" : "", rows, nz, L.A.bs, L.dist ? ", z-slab distributed" : L.rowpart ? ", replicated, products row-partitioned" : "");
+               l, s.cheb_its, L.emin, L.emax, s.n_cheb_fixed ? " (set explicitly)" : "", rows, nz, L.A.bs, L.dist ? ", z-slab distributed" : L.pdist ? ", distributed by node planes (operator replicated)" : "");
     }
     add("    KSP solver for S = A11 - A10 inv(A00) A01: (saddle_fieldsplit_p_) preonly; PC %s on Mpscaled (rows=%d, nonzeros=%lld)\n",
         s.p_pc == 0 ? "bjacobi, one block per GPU, ilu(0) in natural ordering" : "jacobi", c->Mp.n, (long long)c->Mp.nnz);
@@ -477,6 +496,20 @@ int xsb_ksp_get_counters(xsb_ctx c, int64_t out[8])
   if (!c || !out) return XSB_ERR_ARG;
   out[0] = c->n_a00; out[1] = c->n_a; out[2] = c->solve_launches; out[3] = c->a00_timed ? (int64_t)(c->a00_ns_sum / c->a00_timed) : 0;
   for (int i = 0; i < 4; ++i) out[4 + i] = c->a00_mode[i];
+  return XSB_OK;
+}
+int xsb_ksp_get_profile(xsb_ctx c, double *ms, int64_t *count, int cap, int *ncat)
+{
+  if (!c || !ms || !count || !ncat) return XSB_ERR_ARG;
+  *ncat = PROF_N;
+  for (int i = 0; i < PROF_N && i < cap; ++i) { ms[i] = c->prof_ms[i]; count[i] = c->prof_cnt[i]; }
+  return XSB_OK;
+}
+int xsb_comm_info(xsb_ctx c, int64_t out[4])
+{
+  if (!c || !out) return XSB_ERR_ARG;
+  out[0] = c->slab.rank; out[1] = c->slab.nranks; out[2] = comm_p2p_active(c); out[3] = 0;
+  for (int l = 0; l < c->nlev; ++l) if (c->lev[l].pdist) out[3] |= 1LL << l;
   return XSB_OK;
 }
 int xsb_comm_unique_id(void *out128) { return comm_unique_id(out128); }
@@ -654,6 +687,18 @@ int xsb_slab_range(int mz, int nranks, int rank, int *k0, int *k1)
   const int q = mz / nranks, r = mz % nranks;
   const int s = rank * q + (rank < r ? rank : r);
   if (k0) *k0 = s; if (k1) *k1 = s + q + (rank < r ? 1 : 0);
+  return XSB_OK;
+}
+
+// Node planes of coarse MG level `depth` below the fine one (depth 0 = first coarse level, mz+1 planes) that rank `rank` of a
+// z-slab partition computes: the planes of its element layers (the last rank also the top plane), halved with every further
+// coarsening (coarse plane K sits on fine plane 2K).  The ranges of all ranks tile [0, planes of the level).
+int xsb_pdist_range(int mz, int nranks, int rank, int depth, int *p0, int *p1)
+{
+  int k0, k1; if (depth < 0 || xsb_slab_range(mz, nranks, rank, &k0, &k1)) return XSB_ERR_ARG;
+  if (rank == nranks - 1) k1 = mz + 1;
+  for (int d = 0; d < depth; ++d) { k0 = (k0 + 1) / 2; k1 = (k1 + 1) / 2; }
+  if (p0) *p0 = k0; if (p1) *p1 = k1;
   return XSB_OK;
 }
 

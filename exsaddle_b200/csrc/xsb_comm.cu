@@ -70,6 +70,7 @@ int comm_init(xsb_ctx c, const void *unique_id, int rank, int nranks)
 
 int comm_destroy(xsb_ctx c)
 {
+  comm_p2p_destroy(c);
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl);
   c->nccl = nullptr;
   return 0;
@@ -82,12 +83,139 @@ int comm_allreduce_sum(xsb_ctx c, double *dev, int n)
   return 0;
 }
 
-// Ghost update of a lattice vector whose planes hold `pd` doubles: this rank's owned planes are local [o0,o1);
-// it needs gb planes below o0 (the top gb owned planes of rank-1) and ga planes at o1 (the bottom ga of rank+1).
-static int halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb, int ga)
+// ------------------------------------------------------------------ peer-memory halo exchange (NVLink / NVSwitch)
+// ncclSend/ncclRecv of a ghost plane costs ~50 us per exchange (measured: fine-level product 164 us at N = 2 against 95 us of
+// arithmetic), and the solve does one in front of every operator product -- far more than the 0.4 - 3 MB of a plane need on
+// NVLink.  So the exchange is ONE kernel over peer memory: every rank owns a small window (cudaMalloc, opened by both
+// neighbours through cudaIpc handles exchanged once with ncclAllGather); the kernel
+//   A. copies this rank's boundary planes straight into the neighbours' windows (stores over NVLink), fences, and the last
+//      block to finish stores the exchange's sequence number into the neighbours' flag words (st.release.sys);
+//   B. waits (ld.acquire.sys) until both neighbours' sequence numbers have arrived in its OWN flag words, then copies the
+//      window slots into the ghost planes of the vector.
+// Windows are double-buffered by the parity of the sequence number: a rank can only start exchange s+2 after it finished
+// part B of s+1, i.e. after the neighbour finished part A of s+1, which is stream-ordered behind the neighbour's whole kernel s
+// -- so slot s%2 is free again, without acknowledgements.  The sequence number lives in device memory (read and advanced by
+// the kernel), so the kernel replays correctly inside CUDA graphs.  A wait that exceeds ~2 s (a neighbour died) raises a
+// sticky error word instead of hanging the GPU; xsb_ksp_solve reports it.
+struct P2P {
+  bool on = false;
+  char *win = nullptr, *peer_lo = nullptr, *peer_hi = nullptr;   // my window, the windows of rank-1 / rank+1
+  unsigned long long *ctl = nullptr;                               // local control words: [0] sequence, [1] part-A blocks done, [2] error, [3] part-B blocks done
+  size_t slot_bytes = 0;
+};
+enum { P2P_HDR = 256 };   // window: [flag from below, flag from above, pad][from-below slot 0,1][from-above slot 0,1]
+struct P2PDev { unsigned long long *ctl; char *win, *peer_lo, *peer_hi; size_t slot_bytes; };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{ unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{ asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256) k_halo_p2p(double *__restrict__ v, int64_t pd, int o0, int o1, int gb, int ga, P2PDev w)
+{
+  __shared__ unsigned long long s_seq; __shared__ int s_err;
+  const bool lo = w.peer_lo != nullptr, hi = w.peer_hi != nullptr;
+  if (threadIdx.x == 0) { s_seq = *(volatile unsigned long long *)&w.ctl[0] + 1; s_err = (int)*(volatile unsigned long long *)&w.ctl[2]; }
+  __syncthreads();
+  const unsigned long long seq = s_seq; const int slot = (int)(seq & 1);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  // A: my bottom `ga` owned planes are the neighbour below's ghost planes above; my top `gb` owned planes the ghosts below of the neighbour above
+  if (lo) { double *dst = (double *)(w.peer_lo + P2P_HDR + (size_t)(2 + slot) * w.slot_bytes); const double *src = v + (int64_t)o0 * pd; for (int64_t i = tid; i < ga * pd; i += nth) dst[i] = src[i]; }
+  if (hi) { double *dst = (double *)(w.peer_hi + P2P_HDR + (size_t)(0 + slot) * w.slot_bytes); const double *src = v + (int64_t)(o1 - gb) * pd; for (int64_t i = tid; i < gb * pd; i += nth) dst[i] = src[i]; }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&w.ctl[1], 1ULL) == gridDim.x - 1) {   // every block's planes are on their way: publish
+      w.ctl[1] = 0; __threadfence_system();
+      if (lo) st_release_sys((unsigned long long *)w.peer_lo + 1, seq);   // I am the rank ABOVE rank-1
+      if (hi) st_release_sys((unsigned long long *)w.peer_hi + 0, seq);
+    }
+    // B: wait for both neighbours' planes of this exchange
+    if (!s_err) {
+      const long long t0 = clock64(); const unsigned long long *fl = (const unsigned long long *)w.win;
+      while ((lo && ld_acquire_sys(fl + 0) < seq) || (hi && ld_acquire_sys(fl + 1) < seq)) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(&w.ctl[2], 1ULL); break; }
+        __nanosleep(100);
+      }
+    }
+  }
+  __syncthreads();
+  if (lo) { const double *src = (const double *)(w.win + P2P_HDR + (size_t)(0 + slot) * w.slot_bytes); double *dst = v + (int64_t)(o0 - gb) * pd; for (int64_t i = tid; i < gb * pd; i += nth) dst[i] = __ldcg(src + i); }
+  if (hi) { const double *src = (const double *)(w.win + P2P_HDR + (size_t)(2 + slot) * w.slot_bytes); double *dst = v + (int64_t)o1 * pd; for (int64_t i = tid; i < ga * pd; i += nth) dst[i] = __ldcg(src + i); }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&w.ctl[3], 1ULL) == gridDim.x - 1) { w.ctl[3] = 0; *(volatile unsigned long long *)&w.ctl[0] = seq; }   // the last block closes the exchange
+}
+
+static void p2p_release(xsb_ctx c, bool collective)
+{
+  P2P *p = (P2P *)c->p2p; if (!p) return;
+  cudaStreamSynchronize(c->stream);
+  if (p->peer_lo) cudaIpcCloseMemHandle(p->peer_lo);
+  if (p->peer_hi) cudaIpcCloseMemHandle(p->peer_hi);
+  if (collective && c->nccl && p->ctl) { g_nccl.AllReduce(p->ctl + 4, p->ctl + 4, 1, ncclFloat64_, ncclSum_, (ncclComm_t)c->nccl, c->stream); cudaStreamSynchronize(c->stream); }   // nobody frees a window a neighbour still maps
+  if (p->win) cudaFree(p->win);
+  if (p->ctl) cudaFree(p->ctl);
+  delete p; c->p2p = nullptr;
+}
+
+// Collective (called by xsb_assemble on every rank once the local lattice is known): windows sized for the largest message,
+// two velocity planes of the fine lattice.  -xsb_p2p 0 keeps ncclSend / ncclRecv.
+int comm_p2p_setup(xsb_ctx c)
+{
+  const Slab &S = c->slab; const Lattice &L = c->lat;
+  if (S.nranks == 1) return 0;
+  if (!c->opt.integer("xsb_p2p", 1)) { p2p_release(c, true); return 0; }
+  const size_t need = (((size_t)2 * L.nsd * L.NX * L.NY * sizeof(double)) + 255) & ~(size_t)255;
+  P2P *p = (P2P *)c->p2p;
+  if (p && p->on && p->slot_bytes == need) return 0;   // NX, NY are global: every rank takes the same branch
+  p2p_release(c, true);
+  p = new P2P(); c->p2p = p; p->slot_bytes = need;
+  CUDA_OK(cudaMalloc(&p->win, P2P_HDR + 4 * need)); CUDA_OK(cudaMemsetAsync(p->win, 0, P2P_HDR + 4 * need, c->stream));
+  CUDA_OK(cudaMalloc(&p->ctl, 64)); CUDA_OK(cudaMemsetAsync(p->ctl, 0, 64, c->stream));
+  cudaIpcMemHandle_t mine; CUDA_OK(cudaIpcGetMemHandle(&mine, p->win));
+  char *hd = nullptr; CUDA_OK(cudaMalloc(&hd, sizeof(mine) * S.nranks));
+  CUDA_OK(cudaMemcpyAsync(hd + sizeof(mine) * S.rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(g_nccl.AllGather(hd + sizeof(mine) * S.rank, hd, sizeof(mine), 0 /* ncclInt8 */, (ncclComm_t)c->nccl, c->stream));   // also orders every rank's memset before anyone's first push
+  std::vector<cudaIpcMemHandle_t> all(S.nranks);
+  CUDA_OK(cudaMemcpyAsync(all.data(), hd, sizeof(mine) * S.nranks, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaFree(hd));
+  cudaError_t e = cudaSuccess;
+  if (S.rank > 0) e = cudaIpcOpenMemHandle((void **)&p->peer_lo, all[S.rank - 1], cudaIpcMemLazyEnablePeerAccess);
+  if (e == cudaSuccess && S.rank < S.nranks - 1) e = cudaIpcOpenMemHandle((void **)&p->peer_hi, all[S.rank + 1], cudaIpcMemLazyEnablePeerAccess);
+  // all ranks must agree on the transport: one that cannot map its neighbours sends everybody back to NCCL
+  double ok = e == cudaSuccess ? 0.0 : 1.0; double *okd = (double *)(p->ctl + 5);
+  if (e != cudaSuccess) cudaGetLastError();
+  CUDA_OK(cudaMemcpyAsync(okd, &ok, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(g_nccl.AllReduce(okd, okd, 1, ncclFloat64_, ncclSum_, (ncclComm_t)c->nccl, c->stream));
+  CUDA_OK(cudaMemcpyAsync(&ok, okd, sizeof(double), cudaMemcpyDeviceToHost, c->stream)); CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaMemsetAsync(okd, 0, sizeof(double), c->stream));
+  p->on = ok == 0.0;
+  if (!p->on && c->opt.integer("xsb_p2p", 1) > 1) return xsb_fail(c, XSB_ERR_NCCL, "-xsb_p2p 2: peer-memory windows could not be mapped (%s)", cudaGetErrorString(e));
+  return 0;
+}
+int comm_p2p_active(xsb_ctx c) { const P2P *p = (const P2P *)c->p2p; return p && p->on; }
+int comm_p2p_check(xsb_ctx c)
+{
+  const P2P *p = (const P2P *)c->p2p; if (!p || !p->on) return 0;
+  unsigned long long err = 0; CUDA_OK(cudaMemcpyAsync(&err, p->ctl + 2, sizeof(err), cudaMemcpyDeviceToHost, c->stream)); CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (err) return xsb_fail(c, XSB_ERR_NCCL, "peer-memory halo exchange timed out waiting for a neighbour rank");
+  return 0;
+}
+void comm_p2p_destroy(xsb_ctx c) { p2p_release(c, false); }   // tear-down is not collective: the windows are idle, no barrier
+
+// Ghost update of a lattice vector whose planes hold `pd` doubles: this rank's owned planes are [o0,o1) in the vector's own
+// plane numbering; it needs gb planes below o0 (the top gb owned planes of rank-1) and ga planes at o1 (the bottom ga of rank+1).
+int comm_halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb, int ga)
 {
   const Slab &S = c->slab;
   if (S.nranks == 1) return 0;
+  const P2P *p = (const P2P *)c->p2p;
+  if (p && p->on && (size_t)((gb > ga ? gb : ga) * pd) * sizeof(double) <= p->slot_bytes) {
+    P2PDev w{p->ctl, p->win, p->peer_lo, p->peer_hi, p->slot_bytes};
+    int64_t blocks = ((gb > ga ? gb : ga) * pd + 2047) / 2048; if (blocks > 64) blocks = 64; if (blocks < 1) blocks = 1;
+    k_halo_p2p<<<(unsigned)blocks, 256, 0, c->stream>>>(v, pd, o0, o1, gb, ga, w); KERNEL_OK();
+    return 0;
+  }
   ncclComm_t comm = (ncclComm_t)c->nccl;
   NCCL_OK(g_nccl.GroupStart());
   if (S.rank > 0) {
@@ -101,6 +229,7 @@ static int halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb,
   NCCL_OK(g_nccl.GroupEnd());
   return 0;
 }
+static int halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb, int ga) { return comm_halo_planes(c, v, pd, o0, o1, gb, ga); }
 int comm_halo_u(xsb_ctx c, double *u) { const Lattice &L = c->lat; return halo_planes(c, u, (int64_t)L.nsd * L.NX * L.NY, c->slab.ou0, c->slab.ou1, 2, 1); }
 int comm_halo_p(xsb_ctx c, double *p) { const Lattice &L = c->lat; return halo_planes(c, p, (int64_t)L.PX * L.PY, c->slab.op0, c->slab.op1, 1, 1); }
 int comm_halo_full(xsb_ctx c, double *x)
@@ -143,14 +272,19 @@ int comm_bcast_planes(xsb_ctx c, double *glob, int64_t pd, int nplanes_glob)
   return 0;
 }
 
-// Row-partitioned product on a replicated level: rank r holds fresh values for planes [r cp, (r+1) cp) of `glob`, cp = ceil(n / N)
-// (equal chunks: the vector is allocated with N cp planes, the tail beyond the lattice is padding), so the exchange is ONE
-// in-place ncclAllGather instead of N grouped broadcasts.
-int comm_allgather_planes(xsb_ctx c, double *glob, int64_t pd, int nplanes)
+// A coarse vector whose planes [p0[r], p1[r]) were computed by rank r (restriction from a plane-distributed level) becomes
+// replicated: every rank broadcasts its planes (one group).
+int comm_bcast_plane_ranges(xsb_ctx c, double *glob, int64_t pd, const int *p0, const int *p1)
 {
   const Slab &S = c->slab;
   if (S.nranks == 1) return 0;
-  const int64_t cp = (nplanes + S.nranks - 1) / S.nranks;
-  NCCL_OK(g_nccl.AllGather(glob + (int64_t)S.rank * cp * pd, glob, (size_t)(cp * pd), ncclFloat64_, (ncclComm_t)c->nccl, c->stream));
+  ncclComm_t comm = (ncclComm_t)c->nccl;
+  NCCL_OK(g_nccl.GroupStart());
+  for (int r = 0; r < S.nranks; ++r) {
+    if (p1[r] <= p0[r]) continue;
+    double *p = glob + (int64_t)p0[r] * pd;
+    NCCL_OK(g_nccl.Broadcast(p, p, (size_t)((int64_t)(p1[r] - p0[r]) * pd), ncclFloat64_, r, comm, c->stream));
+  }
+  NCCL_OK(g_nccl.GroupEnd());
   return 0;
 }

@@ -186,6 +186,175 @@ k_ilu0_solve(int nw, int np, const int *__restrict__ off, const int *__restrict_
   }
 }
 
+// ------------------------------------------------------------------ line-pipelined triangular solves (default)
+// The wavefront kernel above needs a cluster barrier and an L2 round trip per wavefront: 2.45 ms per apply at 64^3 and
+// 7.2 ms on a 128^3 two-slab block (13 % of that solve), 100 x off the time the factors take to stream.  The same
+// sequential sweep is reorganised so that the dependent chain runs through registers and shared memory:
+//   * one CTA per pressure-node plane k, one thread per node line (j, k); a thread marches along i keeping x(i-1) in a
+//     register; the three values of line j-1 it needs were produced by the neighbouring thread one to three steps earlier
+//     and travel through a 4-deep ring in shared memory -- one block barrier per step (step t handles i = t - 2 j);
+//   * the nine values of plane k-1 come from the CTA below, which runs a few steps ahead; they are fetched from L2 four steps
+//     before use into a register ring, so the L2 latency is off the chain (hand-over protocol: see "the value is the flag");
+//   * the factors are repacked at set-up into one 128-byte record per row, ordered (plane, step, line): a thread streams
+//     its records with cp.async three steps ahead (prefetched into L2 32 steps ahead).
+// The backward sweep is the forward sweep on the mirrored lattice (i, j, k -> px-1-i, ...).  Per row the operations and
+// their order are those of MatSolve_SeqAIJ (ascending columns forward, descending backward): results equal the wavefront
+// kernel's bit for bit.  Chain length: (px + 2 py) steps of ~0.15 us for the first plane + ~12 steps of lag per plane.
+#define ILUP_PF 4      // register-ring prefetch distance of the plane-below values (steps; a step is ~0.4 us, an L2 round trip ~0.7 us)
+#define ILUP_D 3       // cp.async distance of the factor records (steps); ring of ILUP_D + 1 slots
+struct IluPipe { int px, py, pz, S, W; };
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu_u32(unsigned *p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void cp_async16(void *smem, const void *g) { const unsigned sa = (unsigned)__cvta_generic_to_shared(smem); asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(g) : "memory"); }
+__host__ __device__ __forceinline__ int ilup_jlo(int s, int px) { const int v = s - (px - 1); return v <= 0 ? 0 : (v + 1) >> 1; }
+
+// one 128-byte record per row and direction: [0..12] factors of the 13 earlier neighbours in sweep order, [13] 1/pivot (backward)
+__global__ void k_ilup_pack(IluPipe P, const int *__restrict__ ia, const int *__restrict__ diag, const double *__restrict__ lu, double *__restrict__ packf, double *__restrict__ packb)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= P.px * P.py * P.pz) return;
+  const BoxPattern pat{P.px, P.py, P.pz, 0};
+  const int i = row % P.px, j = (row / P.px) % P.py, k = row / (P.px * P.py);
+  for (int dir = 0; dir < 2; ++dir) {
+    const int ib = dir ? P.px - 1 - i : i, jb = dir ? P.py - 1 - j : j, kb = dir ? P.pz - 1 - k : k;
+    const int st = ib + 2 * jb;
+    double *rec = (dir ? packb : packf) + ((((int64_t)kb * P.S + st) * P.W) + (jb - ilup_jlo(st, P.px))) * 16;
+    for (int u = 0; u < 13; ++u) {
+      const int di = u < 12 ? u % 3 - 1 : -1, dj = u < 9 ? (u / 3) % 3 - 1 : (u < 12 ? -1 : 0), dk = u < 9 ? -1 : 0;
+      const int nib = ib + di, njb = jb + dj, nkb = kb + dk;
+      double v = 0.0;
+      if (nib >= 0 && nib < P.px && njb >= 0 && njb < P.py && nkb >= 0 && nkb < P.pz) {
+        const int ni = dir ? P.px - 1 - nib : nib, nj = dir ? P.py - 1 - njb : njb, nk = dir ? P.pz - 1 - nkb : nkb;
+        v = lu[ia[row] + box_slot(pat, i, j, k, ni, nj, nk)];
+      }
+      rec[u] = v;
+    }
+    rec[13] = dir ? lu[diag[row]] : 0.0; rec[14] = 0.0; rec[15] = 0.0;
+  }
+}
+
+// Hand-over between planes without flags or fences: THE VALUE IS THE FLAG.  Both sweeps write into arrays that a small kernel
+// has filled with a sentinel (a quiet NaN with a payload no computation produces) beforehand; a consumer that fetches a value
+// of the plane below and finds the sentinel fetches it again (ld.relaxed.gpu, served by L2) until the real value has
+// arrived.  An 8-byte store is single-copy atomic and nothing else depends on it, so no release / acquire pair is needed (a
+// first version published step counters with st.release.gpu: the gpu-scope fence behind it cost ~2.8 us per publication and
+// bounded the whole pipeline).  The forward sweep writes y into a scratch vector, the backward sweep reads y and writes x,
+// so "not yet written" is distinguishable in both.  A fetch that waits longer than ~2 s raises a sticky error word.
+#define ILUP_SENTINEL 0x7FF8DEADBEEF1234ULL
+__device__ __forceinline__ double ld_relaxed_gpu_f64(const double *p) { double v; asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_relaxed_gpu_f64(double *p, double v) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ bool ilup_missing(double v) { return (unsigned long long)__double_as_longlong(v) == ILUP_SENTINEL; }
+__device__ __noinline__ double ilup_refetch(const double *p, unsigned *err)
+{
+  const long long t0 = clock64(); double v;
+  do { v = ld_relaxed_gpu_f64(p); if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u); return 0.0; } } while (ilup_missing(v));
+  return v;
+}
+__global__ void k_ilup_fill(int64_t n, double *a, double *b)
+{
+  const double s = __longlong_as_double((long long)ILUP_SENTINEL);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { a[i] = s; b[i] = s; }
+}
+
+// rhs: right-hand side of the sweep (b forward, y backward); out: the vector this sweep writes and reads the plane below from
+template <bool BWD>
+__device__ __forceinline__ void ilup_sweep(const IluPipe P, const int kb, const double *__restrict__ pack, const double *__restrict__ rhs, double *out,
+                                           unsigned *err, double2 *rows, double *xs)
+{
+  const int T = (int)blockDim.x, t = (int)threadIdx.x, jb = t;
+  for (int a = 0; a < 4; ++a) xs[t * 4 + a] = 0.0;
+  __syncthreads();
+  const bool line = jb < P.py;
+  const int64_t plane = (int64_t)P.px * P.py;
+  auto ridx = [&](int ib, int jj, int kk) -> int64_t {
+    const int i = BWD ? P.px - 1 - ib : ib, j = BWD ? P.py - 1 - jj : jj, k = BWD ? P.pz - 1 - kk : kk;
+    return i + (int64_t)j * P.px + (int64_t)k * plane; };
+  double w[3][3], ring[ILUP_PF][4], xprev = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) w[a][b] = 0.0;
+#pragma unroll
+  for (int a = 0; a < ILUP_PF; ++a) for (int b = 0; b < 4; ++b) ring[a][b] = 0.0;
+  const double *pk = pack + (int64_t)kb * P.S * P.W * 16;
+  // addresses advance by one node per step: element `ib` of a line sits at base + dx * ib
+  const int dx = BWD ? -1 : 1;
+  const double *xb0 = out + ridx(0, jb > 0 ? jb - 1 : 0, kb > 0 ? kb - 1 : 0), *xb1 = out + ridx(0, line ? jb : 0, kb > 0 ? kb - 1 : 0), *xb2 = out + ridx(0, jb + 1 < P.py ? jb + 1 : 0, kb > 0 ? kb - 1 : 0);
+  double *xown = out + ridx(0, line ? jb : 0, kb);
+  const double *rown = rhs + ridx(0, line ? jb : 0, kb);
+  const bool v0 = line && kb > 0 && jb > 0, v1 = line && kb > 0, v2 = line && kb > 0 && jb + 1 < P.py;
+  for (int s0 = -2 * ILUP_PF; s0 < P.S; s0 += ILUP_PF) {
+#pragma unroll
+    for (int u = 0; u < ILUP_PF; ++u) {
+      const int s = s0 + u, ib = s - 2 * jb;
+      // values fetched ILUP_PF steps ago for this step: plane kb-1 at position ib+1 of the lines jb-1, jb, jb+1 (fetched again if they
+      // had not been written yet), and the right-hand side
+      {
+        double n0 = ring[u][0], n1 = ring[u][1], n2 = ring[u][2];
+        if (ilup_missing(n0)) n0 = ilup_refetch(xb0 + dx * (ib + 1), err);
+        if (ilup_missing(n1)) n1 = ilup_refetch(xb1 + dx * (ib + 1), err);
+        if (ilup_missing(n2)) n2 = ilup_refetch(xb2 + dx * (ib + 1), err);
+        w[0][0] = w[0][1]; w[0][1] = w[0][2]; w[0][2] = n0;
+        w[1][0] = w[1][1]; w[1][1] = w[1][2]; w[1][2] = n1;
+        w[2][0] = w[2][1]; w[2][1] = w[2][2]; w[2][2] = n2;
+      }
+      const double rhs_now = ring[u][3];
+      {   // fetch for step s + ILUP_PF
+        const int ib8 = ib + ILUP_PF, p = ib8 + 1;
+        const bool pv = p >= 0 && p < P.px;
+        ring[u][0] = (pv && v0) ? ld_relaxed_gpu_f64(xb0 + dx * p) : 0.0;
+        ring[u][1] = (pv && v1) ? ld_relaxed_gpu_f64(xb1 + dx * p) : 0.0;
+        ring[u][2] = (pv && v2) ? ld_relaxed_gpu_f64(xb2 + dx * p) : 0.0;
+        const bool rv = line && ib8 >= 0 && ib8 < P.px;
+        ring[u][3] = rv ? (BWD ? __ldcg(rown + dx * ib8) : __ldg(rown + dx * ib8)) : 0.0;
+      }
+      {   // factor record of step s + ILUP_D -> shared memory; of step s + 32 -> L2
+        const int sr = s + ILUP_D, ir = sr - 2 * jb;
+        if (line && ir >= 0 && ir < P.px) {
+          const double *rec = pk + (sr * P.W + (jb - ilup_jlo(sr, P.px))) * 16;
+          double2 *dst = rows + (size_t)((sr & ILUP_D) * 7) * T + t;
+#pragma unroll
+          for (int cc = 0; cc < 7; ++cc) cp_async16(dst + (size_t)cc * T, rec + 2 * cc);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int sp = s + 32, ip = sp - 2 * jb;
+        if (line && ip >= 0 && ip < P.px) prefetch_l2(pk + (sp * P.W + (jb - ilup_jlo(sp, P.px))) * 16);
+      }
+      if (s >= 0 && s < P.S) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(ILUP_D) : "memory");
+        if (line && ib >= 0 && ib < P.px) {
+          const double2 *src = rows + (size_t)((s & ILUP_D) * 7) * T + t;
+          double L[14];
+#pragma unroll
+          for (int cc = 0; cc < 7; ++cc) { const double2 v = src[(size_t)cc * T]; L[2 * cc] = v.x; L[2 * cc + 1] = v.y; }
+          const bool jm = jb > 0;
+          const double q0 = (jm && ib > 0) ? xs[(t - 1) * 4 + ((ib - 1) & 3)] : 0.0;
+          const double q1 = jm ? xs[(t - 1) * 4 + (ib & 3)] : 0.0;
+          const double q2 = (jm && ib + 1 < P.px) ? xs[(t - 1) * 4 + ((ib + 1) & 3)] : 0.0;
+          double acc = rhs_now;
+          acc -= L[0] * w[0][0]; acc -= L[1] * w[0][1]; acc -= L[2] * w[0][2];
+          acc -= L[3] * w[1][0]; acc -= L[4] * w[1][1]; acc -= L[5] * w[1][2];
+          acc -= L[6] * w[2][0]; acc -= L[7] * w[2][1]; acc -= L[8] * w[2][2];
+          acc -= L[9] * q0; acc -= L[10] * q1; acc -= L[11] * q2;
+          acc -= L[12] * xprev;
+          if (BWD) acc *= L[13];
+          st_relaxed_gpu_f64(xown + dx * ib, acc);
+          xs[t * 4 + (ib & 3)] = acc; xprev = acc;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_ilup_solve(IluPipe P, const double *__restrict__ packf, const double *__restrict__ packb, const double *__restrict__ b, double *y, double *x, unsigned *err)
+{
+  extern __shared__ double2 ilup_smem[];
+  const int T = (int)blockDim.x;
+  double2 *rows = ilup_smem; double *xs = (double *)(ilup_smem + (size_t)(ILUP_D + 1) * 7 * T);
+  ilup_sweep<false>(P, (int)blockIdx.x, packf, b, y, err, rows, xs);
+  ilup_sweep<true>(P, P.pz - 1 - (int)blockIdx.x, packb, y, x, err, rows, xs);
+}
+
 // bjacobi block of this rank: rows and columns of the owned pressure planes [op0,op1) of the local lattice, as a
 // 27-point matrix on the owned sub-lattice (PETSc PCBJACOBI: the rank's diagonal block of Mpscaled).
 __global__ void k_own_len(PLat P, int *len)
@@ -261,11 +430,38 @@ int ilu_setup(xsb_ctx c)
   }
   int h = 0; CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
   if (h) return xsb_fail(c, XSB_ERR_BREAKDOWN, "zero pivot in ILU(0) of Mpscaled");
+  // line-pipelined solve (-xsb_ilu_kernel 1, default): needs one resident CTA per plane (they wait for each other)
+  c->ilup_on = false;
+  if (c->opt.integer("xsb_ilu_kernel", 1) == 1 && P.py <= 256) {   // one thread per node line, at most 256 (register budget of the prefetch rings)
+    const int T = ((P.py + 31) / 32) * 32; const size_t smem = (size_t)T * ((ILUP_D + 1) * 7 * 16 + 4 * 8);   // one thread per node line
+    int per_sm = 0, sms = 0;
+    CUDA_OK(cudaFuncSetAttribute(k_ilup_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilup_solve, T, smem));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if (smem <= 200 * 1024 && (int64_t)per_sm * sms >= P.pz) {
+      const int S = P.px + 2 * (P.py - 1); int W = (P.px - 1) / 2 + 2; if (W > P.py) W = P.py;
+      const size_t recs = (size_t)P.pz * S * W * 16;
+      XSB_CHK(dev_alloc(c, &c->ilup_packf, recs)); XSB_CHK(dev_alloc(c, &c->ilup_packb, recs)); XSB_CHK(dev_alloc(c, &c->ilup_prog, (size_t)4)); XSB_CHK(dev_alloc(c, &c->ilup_y, (size_t)np));
+      CUDA_OK(cudaMemsetAsync(c->ilup_prog, 0, sizeof(unsigned) * 4, st));
+      c->ilup_dims[0] = P.px; c->ilup_dims[1] = P.py; c->ilup_dims[2] = P.pz; c->ilup_dims[3] = S; c->ilup_dims[4] = W; c->ilup_dims[5] = T; c->ilup_smem = smem;
+      IluPipe Q{P.px, P.py, P.pz, S, W};
+      k_ilup_pack<<<(np + 127) / 128, 128, 0, st>>>(Q, M.ia, diag, c->mp_lu, c->ilup_packf, c->ilup_packb); KERNEL_OK();
+      c->ilup_on = true;
+    }
+  }
   return 0;
 }
 
 int ilu_apply(xsb_ctx c, const double *b, double *x)
 {
+  if (c->ilup_on) {
+    IluPipe Q{c->ilup_dims[0], c->ilup_dims[1], c->ilup_dims[2], c->ilup_dims[3], c->ilup_dims[4]};
+    if (b == x) return xsb_fail(c, XSB_ERR_ARG, "ILU(0) solve: right-hand side and solution must be different vectors");
+    const int64_t np = (int64_t)Q.px * Q.py * Q.pz;
+    k_ilup_fill<<<(unsigned)((np + 1023) / 1024 > 592 ? 592 : (np + 1023) / 1024), 256, 0, c->stream>>>(np, c->ilup_y, x); KERNEL_OK();
+    k_ilup_solve<<<Q.pz, c->ilup_dims[5], c->ilup_smem, c->stream>>>(Q, c->ilup_packf, c->ilup_packb, b, c->ilup_y, x, c->ilup_prog); KERNEL_OK();
+    return 0;
+  }
   k_ilu0_solve<<<ILU_CLUSTER, ILU_TPB, sizeof(int) * (c->ilu_nlvl + 1), c->stream>>>(c->ilu_nlvl, c->MpOwn.n, c->ilu_lvl_off, c->ilu_rows, c->ilu_fcol, c->ilu_fval, c->ilu_fn,
                                                        c->ilu_bcol, c->ilu_bval, c->ilu_bn, c->ilu_binv, b, x); KERNEL_OK();
   return 0;

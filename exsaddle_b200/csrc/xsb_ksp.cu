@@ -72,7 +72,7 @@ int op_full_mult(xsb_ctx c, const double *x, double *y)
   XSB_CHK(spmv_csr(c, c->A, x, y, c->own_full.off0, c->own_full.len0));
   return spmv_csr(c, c->A, x, y, c->own_full.off1, c->own_full.len1);
 }
-static int full_mult(xsb_ctx c, const double *x, double *y) { c->n_a++; return op_full_mult(c, x, y); }
+static int full_mult(xsb_ctx c, const double *x, double *y) { c->n_a++; XSB_CHK(prof_mark(c, PROF_FULL)); XSB_CHK(op_full_mult(c, x, y)); return prof_mark(c, PROF_OTHER); }
 static int a00_mult(xsb_ctx c, const double *x, double *y) { Epilogue ep; return spmv_a00_fine(c, c->A00, x, y, ep); }
 
 // ------------------------------------------------------------------ KSPSolve_GCR on A00, right PC = PCMG
@@ -125,9 +125,12 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reaso
   if (c->so.pc_type == 4) return fsd_apply(c, r, z);
   // PCApply_FieldSplit_Schur, PC_FIELDSPLIT_SCHUR_FACT_UPPER
   double *yp = z + L.nu;
+  XSB_CHK(prof_mark(c, PROF_ILU));
   if (c->so.p_pc == 0) XSB_CHK(ilu_apply(c, r + L.nu + c->own_p.off0, yp + c->own_p.off0)); else XSB_CHK(vec_pmult(c, L.np, c->mp_idiag, r + L.nu, yp));
+  XSB_CHK(prof_mark(c, PROF_CSR));
   XSB_CHK(comm_halo_p(c, yp));
   XSB_CHK(spmv_csr(c, c->A01, yp, c->fs_tu, c->own_u.off0, c->own_u.len0));
+  XSB_CHK(prof_mark(c, PROF_OTHER));
   XSB_CHK(vec_aypx(c, L.nu, -1.0, r, c->fs_tu));      // t_u = x_u - A01 y_p
   int its = 0, why = 0;
   XSB_CHK(gcr_solve(c, c->fs_tu, z, &its, &why));
@@ -223,6 +226,7 @@ int ksp_release(xsb_ctx c)
   c->red = c->scal = nullptr; c->w_t1 = c->w_t2 = c->xdev = c->bdev = c->idiagA = c->gcr_r = c->fs_tu = nullptr;
   c->mp_lu = c->mp_idiag = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
   c->ilu_fval = c->ilu_bval = c->ilu_binv = nullptr; c->ilu_fn = c->ilu_bn = nullptr; c->MpOwn = Csr();
+  c->ilup_on = false; c->ilup_packf = c->ilup_packb = nullptr; c->ilup_prog = nullptr; c->ilup_y = nullptr;
   c->V.clear(); c->Z.clear(); c->GV.clear(); c->GS.clear();
   for (int l = 0; l < XSB_MAX_LEVELS; ++l) { c->lev[l] = Level(); c->sub[l] = Level(); }
   c->nlev = 0; c->nsub = 0; c->cg_p = c->cg_q = nullptr; c->ksp_ready = false;
@@ -272,6 +276,7 @@ int ksp_solve(xsb_ctx c, const double *b, double *x)
   const int64_t launch0 = c->n_launch;
   auto need = [&](std::vector<double *> &W, int k) -> int { while ((int)W.size() <= k) { double *p = nullptr; c->phase = 1; int rc = dev_alloc(c, &p, (size_t)n); c->phase = 0; if (rc) return rc; W.push_back(p); } return 0; };
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  XSB_CHK(prof_mark(c, PROF_OTHER));
   if (!b) b = c->F;
   XSB_CHK(vec_set(c, n, 0.0, x));          // initial guess is zero
   XSB_CHK(need(c->V, 0));
@@ -337,9 +342,12 @@ int ksp_solve(xsb_ctx c, const double *b, double *x)
     }
     if (!c->reason && c->its >= s.max_it) c->reason = -3;
   }
+  XSB_CHK(prof_mark(c, PROF_OTHER));
   CUDA_OK(cudaEventRecord(c->ev1, c->stream)); CUDA_OK(cudaEventSynchronize(c->ev1));
   CUDA_OK(cudaEventElapsedTime(&c->solve_ms, c->ev0, c->ev1));
   c->solve_launches = c->n_launch - launch0;
   XSB_CHK(spmv_collect_timing(c));
-  return 0;
+  if (c->ilup_on) { unsigned e = 0; CUDA_OK(cudaMemcpyAsync(&e, c->ilup_prog, sizeof(e), cudaMemcpyDeviceToHost, c->stream)); CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (e) return xsb_fail(c, XSB_ERR_BREAKDOWN, "pipelined ILU(0) solve: a plane waited more than 2 s for the plane below (NaN right-hand side?)"); }
+  return comm_p2p_check(c);
 }

@@ -58,25 +58,34 @@ __global__ void k_prolong_add(int fnx, int fny, int z0, int z1, int fz0, int cnx
 #pragma unroll
   for (int d = 0; d < BS; ++d) xf[BS * f + d] += acc[d];
 }
+// Slabs.  The fine level lives on the rank's local lattice (ghost planes refreshed in front of every product); a plane-
+// distributed coarse level (Level::pdist) keeps global indexing and is current on the planes [rp0-1, rp1+1): its products
+// exchange their OUTPUT planes, so a residual or an iterate handed to the transfers already carries valid neighbour planes.
 int mg_restrict(xsb_ctx c, const Level &F, const Level &C, const double *rf, double *bc)
 {
   const Slab &S = c->slab;
   int fz0 = 0, K0 = 0, K1 = C.nz;
-  if (F.dist) {   // owned coarse planes only; the ghost plane below is refreshed first, the result is replicated after
+  if (F.dist) {   // owned coarse planes only; the ghost plane below is refreshed first
     XSB_CHK(comm_halo_u(c, const_cast<double *>(rf)));
     fz0 = 2 * S.e0; K0 = S.k0; K1 = S.rank == S.nranks - 1 ? C.nz : S.k1;
-  }
+  } else if (F.pdist) { K0 = (F.rp0 + 1) / 2; K1 = (F.rp1 + 1) / 2; }   // coarse plane K sits on fine plane 2K: owned with it
   const int64_t nc = (int64_t)C.nx * C.ny * (K1 - K0);
-  if (c->nsd == 3) k_restrict<3><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, fz0, C.nx, C.ny, K0, K1, rf, bc);
-  else k_restrict<2><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, fz0, C.nx, C.ny, K0, K1, rf, bc);
-  KERNEL_OK();
-  if (F.dist) XSB_CHK(comm_bcast_planes(c, bc, (int64_t)c->nsd * C.nx * C.ny, C.nz));
+  if (nc > 0) {
+    if (c->nsd == 3) k_restrict<3><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, fz0, C.nx, C.ny, K0, K1, rf, bc);
+    else k_restrict<2><<<nblk(nc, 128), 128, 0, c->stream>>>(F.nx, F.ny, F.nz, fz0, C.nx, C.ny, K0, K1, rf, bc);
+    KERNEL_OK();
+  }
+  if (C.pdist) return 0;   // the right-hand side is only read on owned rows
+  if (F.dist) XSB_CHK(comm_bcast_planes(c, bc, (int64_t)c->nsd * C.nx * C.ny, C.nz));   // replicated coarse level
+  else if (F.pdist) XSB_CHK(comm_bcast_plane_ranges(c, bc, (int64_t)c->nsd * C.nx * C.ny, F.cr0.data(), F.cr1.data()));
   return 0;
 }
 int mg_prolong_add(xsb_ctx c, const Level &F, const Level &C, const double *xc, double *xf)
 {
   const Slab &S = c->slab;
-  const int z0 = F.dist ? S.ou0 : 0, z1 = F.dist ? S.ou1 : F.nz, fz0 = F.dist ? 2 * S.e0 : 0;
+  int z0 = 0, z1 = F.nz, fz0 = 0;
+  if (F.dist) { z0 = S.ou0; z1 = S.ou1; fz0 = 2 * S.e0; }
+  else if (F.pdist) { z0 = F.rp0 - 1 < 0 ? 0 : F.rp0 - 1; z1 = F.rp1 + 1 > F.nz ? F.nz : F.rp1 + 1; }   // neighbour planes too: their coarse parents are current on this rank
   const int64_t nf = (int64_t)F.nx * F.ny * (z1 - z0);
   if (c->nsd == 3) k_prolong_add<3><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, z0, z1, fz0, C.nx, C.ny, xc, xf);
   else k_prolong_add<2><<<nblk(nf), 256, 0, c->stream>>>(F.nx, F.ny, z0, z1, fz0, C.nx, C.ny, xc, xf);
@@ -359,12 +368,16 @@ __global__ void k_cheb_first_zero(int64_t n, double scale, const double *__restr
 static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, double *y, const Epilogue &ep)
 {
   if (fine) return spmv_a00_fine(c, L.A, x, y, ep);
-  if (!L.rowpart) return spmv_baij(c, L.A, x, y, ep);
-  // replicated level, row-partitioned product: this rank computes its share of the node planes (rows and fused
-  // epilogue are per row, so the values are bitwise those of the replicated product), then all ranks exchange planes
+  const int lcat = PROF_LVL + (int)(&L - (&L >= c->sub && &L < c->sub + XSB_MAX_LEVELS ? c->sub : c->lev));
+  XSB_CHK(prof_mark(c, lcat));
+  if (!L.pdist) { XSB_CHK(spmv_baij(c, L.A, x, y, ep)); return prof_mark(c, PROF_OTHER); }
+  // plane-distributed level: this rank computes the rows of its node planes (rows and fused epilogue are per row, so the
+  // values are bitwise those of the one-GPU product) and trades one plane of the result with each neighbour
   const int pn = L.nx * L.ny;
   XSB_CHK(spmv_baij(c, L.A, x, y, ep, L.rp0 * pn, (L.rp1 - L.rp0) * pn));
-  return comm_allgather_planes(c, y, (int64_t)L.A.bs * pn, L.nz);
+  XSB_CHK(prof_mark(c, PROF_CHALO));
+  XSB_CHK(comm_halo_planes(c, y, (int64_t)L.A.bs * pn, L.rp0, L.rp1, 1, 1));
+  return prof_mark(c, PROF_OTHER);
 }
 // set-up products (eigenvalue estimate): not counted; slab levels refresh ghosts and compute owned rows only
 static int level_spmv(xsb_ctx c, const Level &L, const double *x, double *y)
@@ -389,7 +402,11 @@ static int cheb_smooth(xsb_ctx c, Level &L, bool fine, int its, bool x_is_zero)
   const double scale = 2.0 / (L.emax + L.emin), alpha = 1.0 - scale * L.emin, mu = 1.0 / alpha, omegaprod = 2.0 / alpha;
   double ckm1 = 1.0, ck = mu;
   double *pkm1 = L.x, *pk = L.w0, *pkp1 = L.w1;
-  if (x_is_zero) {   // r = b - A*0 = b exactly: skip the product (bitwise identical)
+  if (x_is_zero && L.pdist) {   // owned planes, then the neighbours' (the right-hand side is only current on owned rows)
+    const int64_t pd = (int64_t)L.A.bs * L.nx * L.ny, o = L.rp0 * pd, m = (L.rp1 - L.rp0) * pd;
+    k_cheb_first_zero<<<nblk(m) > 2368 ? 2368 : nblk(m), 256, 0, c->stream>>>(m, scale, L.idiag + o, L.b + o, pk + o); KERNEL_OK();
+    XSB_CHK(comm_halo_planes(c, pk, pd, L.rp0, L.rp1, 1, 1));
+  } else if (x_is_zero) {   // r = b - A*0 = b exactly: skip the product (bitwise identical)
     k_cheb_first_zero<<<nblk(n) > 2368 ? 2368 : nblk(n), 256, 0, c->stream>>>(n, scale, L.idiag, L.b, pk); KERNEL_OK();
   } else {
     Epilogue ep; ep.mode = EPI_CHEB_FIRST; ep.b = L.b; ep.idiag = L.idiag; ep.pk = pkm1; ep.s0 = scale;
@@ -416,8 +433,9 @@ static int mg_cycle(xsb_ctx c, Level *H, int l, int top, bool main)
   if (l == 0) {   // coarse grid: preonly + LU  ->  x = A^-1 b
     if (!L.inv) return coarse_pcg(c);   // too large for the dense inverse: solved to LU accuracy by V-cycle-preconditioned CG
     const int n = L.A.nb * L.A.bs;
+    XSB_CHK(prof_mark(c, PROF_LVL));
     k_gemv<<<nblk((int64_t)n * 32), 256, 0, c->stream>>>(n, L.inv, L.b, L.x); KERNEL_OK();
-    return 0;
+    return prof_mark(c, PROF_OTHER);
   }
   Level &C = H[l - 1];
   const bool fine = main && l == top;
@@ -425,9 +443,9 @@ static int mg_cycle(xsb_ctx c, Level *H, int l, int top, bool main)
   XSB_CHK(vec_set(c, n, 0.0, L.x));
   XSB_CHK(cheb_smooth(c, L, fine, c->so.cheb_its, true));                 // pre-smooth
   { Epilogue ep; ep.mode = EPI_RESIDUAL; ep.b = L.b; XSB_CHK(a00_spmv(c, L, fine, L.x, L.r, ep)); }   // r = b - A x
-  XSB_CHK(mg_restrict(c, L, C, L.r, C.b));
+  XSB_CHK(prof_mark(c, PROF_XFER)); XSB_CHK(mg_restrict(c, L, C, L.r, C.b)); XSB_CHK(prof_mark(c, PROF_OTHER));
   XSB_CHK(mg_cycle(c, H, l - 1, top, main));
-  XSB_CHK(mg_prolong_add(c, L, C, C.x, L.x));
+  XSB_CHK(prof_mark(c, PROF_XFER)); XSB_CHK(mg_prolong_add(c, L, C, C.x, L.x)); XSB_CHK(prof_mark(c, PROF_OTHER));
   XSB_CHK(cheb_smooth(c, L, fine, c->so.cheb_its, false));                // post-smooth
   return 0;
 }
@@ -635,23 +653,31 @@ int mg_setup(xsb_ctx c)
     else if (c->no_A && l == levels - 2) XSB_CHK(galerkin_elements(c, C));
     else XSB_CHK(galerkin(c, F, C));
   }
-  // large replicated levels: split the rows of every smoother / residual product over the ranks (-xsb_rowpart_min_nodes): rank r
-  // computes the planes [r cp, (r+1) cp), cp = ceil(nz / N), and ONE in-place all-gather of equal chunks replicates the result
-  // (the vectors such a product writes are allocated with N cp planes)
-  if (dist) {
-    const int64_t min_nodes = c->opt.integer("xsb_rowpart_min_nodes", 100000);
-    for (int l = 1; l < levels - 1; ++l) {
+  // Slabs: the coarse levels below the fine one stay distributed by node planes while they are large (-xsb_pdist_min_nodes) and
+  // every rank keeps at least one plane; their operators are replicated (set-up), their vectors are current only around the
+  // owned planes (Level::pdist).  Smaller levels are replicated and computed redundantly.
+  if (dist && c->opt.integer("xsb_pdist", 1)) {
+    const int64_t min_nodes = c->opt.integer("xsb_pdist_min_nodes", 100000);
+    for (int l = levels - 2; l >= 1; --l) {
       Level &L = c->lev[l];
-      if ((int64_t)L.A.nb < min_nodes || L.nz < S.nranks) continue;
-      const int cp = (L.nz + S.nranks - 1) / S.nranks;
-      L.rowpart = true; L.rp0 = S.rank * cp < L.nz ? S.rank * cp : L.nz; L.rp1 = (S.rank + 1) * cp < L.nz ? (S.rank + 1) * cp : L.nz;
+      if ((int64_t)L.A.nb < min_nodes) break;
+      bool ok = true; int mine0 = 0, mine1 = 0;
+      for (int r = 0; r < S.nranks; ++r) { int p0, p1; xsb_pdist_range(S.mz_glob, S.nranks, r, levels - 2 - l, &p0, &p1); if (p1 - p0 < 1) ok = false; if (r == S.rank) { mine0 = p0; mine1 = p1; } }
+      if (!ok) break;
+      L.pdist = true; L.rp0 = mine0; L.rp1 = mine1;
+    }
+    for (int l = levels - 2; l >= 1; --l) {   // a distributed level above a replicated one gathers the restricted planes
+      Level &L = c->lev[l];
+      if (!L.pdist || c->lev[l - 1].pdist) continue;
+      L.cr0.resize(S.nranks); L.cr1.resize(S.nranks);
+      for (int r = 0; r < S.nranks; ++r) xsb_pdist_range(S.mz_glob, S.nranks, r, levels - 2 - l + 1, &L.cr0[r], &L.cr1[r]);
     }
   }
   for (int l = 0; l < levels; ++l) {
     Level &L = c->lev[l]; const int64_t n = (int64_t)L.A.nb * L.A.bs;
-    const int64_t npad = L.rowpart ? (int64_t)((L.nz + S.nranks - 1) / S.nranks) * S.nranks * L.nx * L.ny * L.A.bs : n;
-    XSB_CHK(dev_alloc(c, &L.x, (size_t)npad)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)npad));
-    XSB_CHK(dev_alloc(c, &L.w0, (size_t)npad)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)npad)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
+    XSB_CHK(dev_alloc(c, &L.x, (size_t)n)); XSB_CHK(dev_alloc(c, &L.b, (size_t)n)); XSB_CHK(dev_alloc(c, &L.r, (size_t)n));
+    XSB_CHK(dev_alloc(c, &L.w0, (size_t)n)); XSB_CHK(dev_alloc(c, &L.w1, (size_t)n)); XSB_CHK(dev_alloc(c, &L.idiag, (size_t)n));
+    if (L.pdist) { CUDA_OK(cudaMemsetAsync(L.b, 0, sizeof(double) * n, c->stream)); CUDA_OK(cudaMemsetAsync(L.r, 0, sizeof(double) * n, c->stream)); CUDA_OK(cudaMemsetAsync(L.w0, 0, sizeof(double) * n, c->stream)); CUDA_OK(cudaMemsetAsync(L.w1, 0, sizeof(double) * n, c->stream)); }
     if (c->no_A && l == levels - 1) XSB_CHK(mf_diag_inv(c, L.idiag)); else XSB_CHK(baij_diag_inv(c, L.A, L.idiag));
   }
   XSB_CHK(coarse_setup(c));

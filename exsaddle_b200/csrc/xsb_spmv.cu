@@ -210,25 +210,35 @@ int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilog
 }
 
 // Fine-level A00 launch with bookkeeping: per-mode launch counters (for the algorithmic byte count) and, with
-// -xsb_time_kernels, a CUDA-event pair recorded on the launching stream around the kernel.  Events are only
-// read back after the solve (spmv_collect_timing), so timing adds no synchronisation to the timed region.
+// -xsb_time_kernels, CUDA events recorded on the launching stream in front of the ghost exchange, in front of the kernel and
+// behind it (prof_mark).  Events are only read back after the solve (spmv_collect_timing), so timing adds no synchronisation.
+int prof_mark(xsb_ctx c, int cat)
+{
+  if (!c->so.time_kernels) return XSB_OK;
+  if (c->ev_used + 1 > c->evpool.size()) { for (int i = 0; i < 1024; ++i) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); c->evpool.push_back(e); } }
+  CUDA_OK(cudaEventRecord(c->evpool[c->ev_used], c->stream));
+  if (c->ev_cat.size() <= c->ev_used) c->ev_cat.resize(c->ev_used + 1024);
+  c->ev_cat[c->ev_used++] = cat;
+  return XSB_OK;
+}
 int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep)
 {
   c->n_a00++; c->a00_mode[ep.mode & 3]++;
-  const bool timed = c->so.time_kernels;
-  if (timed) {
-    if (c->ev_used + 2 > c->evpool.size()) { for (int i = 0; i < 256; ++i) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); c->evpool.push_back(e); } }
-    CUDA_OK(cudaEventRecord(c->evpool[c->ev_used], c->stream));
-  }
+  XSB_CHK(prof_mark(c, PROF_FINE_HALO));
   XSB_CHK(comm_halo_u(c, const_cast<double *>(x)));   // ghost planes of the input (no-op on one GPU)
+  XSB_CHK(prof_mark(c, PROF_FINE));
   if (c->so.matrix_free) XSB_CHK(mf_a00_apply(c, x, y, ep));
   else { const int pn = c->lat.NX * c->lat.NY; XSB_CHK(spmv_baij(c, A, x, y, ep, c->slab.ou0 * pn, (c->slab.ou1 - c->slab.ou0) * pn)); }
-  if (timed) { CUDA_OK(cudaEventRecord(c->evpool[c->ev_used + 1], c->stream)); c->ev_used += 2; }
-  return XSB_OK;
+  return prof_mark(c, PROF_OTHER);
 }
 int spmv_collect_timing(xsb_ctx c)
 {
-  for (size_t i = 0; i + 1 < c->ev_used; i += 2) { float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, c->evpool[i], c->evpool[i + 1])); c->a00_ns_sum += 1e6 * (double)ms; c->a00_timed++; }
+  for (int i = 0; i < PROF_N; ++i) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+  for (size_t i = 0; i + 1 < c->ev_used; ++i) {
+    float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, c->evpool[i], c->evpool[i + 1]));
+    const int cat = c->ev_cat[i]; c->prof_ms[cat] += ms; c->prof_cnt[cat]++;
+    if (cat == PROF_FINE) { c->a00_ns_sum += 1e6 * (double)ms; c->a00_timed++; }
+  }
   c->ev_used = 0;
   return XSB_OK;
 }

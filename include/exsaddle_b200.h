@@ -101,6 +101,8 @@ int xsb_pc_apply(xsb_ctx ctx, const double *r, double *z);        /* PCApply of 
 int xsb_pc_apply_dev(xsb_ctx ctx, const double *r, double *z);
 int xsb_pc_mg_apply(xsb_ctx ctx, const double *b, double *x);     /* PCApply_MG on A00 (one V-cycle), host pointers */
 int xsb_pc_schur_apply(xsb_ctx ctx, const double *b, double *x);  /* fieldsplit_p PC on Mpscaled, host pointers */
+/* measurement aid: average device time (ms) of `reps` pressure-block solves on resident vectors */
+int xsb_time_pc_schur(xsb_ctx ctx, int reps, double *ms_per_apply);
 int xsb_mg_restrict(xsb_ctx ctx, int coarse_level, const double *rf, double *bc);     /* MatRestrict */
 int xsb_mg_interpolate_add(xsb_ctx ctx, int coarse_level, const double *xc, double *xf); /* MatInterpolateAdd */
 
@@ -119,6 +121,13 @@ int xsb_ksp_view(xsb_ctx ctx, char *buf, int buflen);
    every such launch when -xsb_time_kernels is set; read back after the solve, no extra synchronisation)
    [4..7] fine-level A00 launches by fused epilogue: plain y=Ax, residual b-Ax, first Chebyshev step, Chebyshev step */
 int xsb_ksp_get_counters(xsb_ctx ctx, int64_t out[8]);
+/* -xsb_time_kernels: device time of the last solve by category (the -log_view stages a PETSc user would read; events on the
+   launching stream cut the solve into stretches, each booked on one category).  ms[i], count[i] for i < min(cap, *ncat):
+   0 Krylov vector kernels + host gaps, 1 ghost exchange in front of fine-level A00 products, 2 fine-level A00 kernels,
+   3+l products on MG level l (l < 10; level 0: the coarse solve), 13 plane exchange behind products of distributed coarse
+   levels, 14 restriction / interpolation (with their exchanges), 15 pressure-block ILU(0) solves, 16 full-operator products
+   of the outer Krylov method, 17 ghost exchange + A01 product of the fieldsplit */
+int xsb_ksp_get_profile(xsb_ctx ctx, double *ms, int64_t *count, int cap, int *ncat);
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on, for event timing by the caller */
 int xsb_get_stream(xsb_ctx ctx, void **stream);
 
@@ -155,12 +164,19 @@ int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, in
 /* Element z-range [k0,k1) owned by `rank` of `nranks` (elements split like the reference's pressure rule,
    femixedspace.c:1231-1240: mz/nranks each, remainder to the low ranks). */
 int xsb_slab_range(int mz, int nranks, int rank, int *k0, int *k1);
+/* Node planes [p0,p1) of coarse velocity-MG level `depth` below the fine level (0 = first coarse level, mz+1 planes) whose
+   rows `rank` computes when the level is distributed: the planes of its element layers, halved per coarsening (PETSc
+   analogue: the DMDA ownership of the coarsened DM, exSaddle.c:408-422 / DMCoarsen).  All ranks' ranges tile the level. */
+int xsb_pdist_range(int mz, int nranks, int rank, int depth, int *p0, int *p1);
 /* host-only: the partition xsb_get_partition reports, computed from the mesh alone (same out[12] layout) */
 int xsb_slab_layout(int nsd, int mx, int my, int mz, int nranks, int rank, int64_t out[12]);
 /* NCCL bootstrap (one process per GPU; replaces MPI_Init/PETSC_COMM_WORLD of the reference, femixedspace.c:645,684):
    rank 0 calls xsb_comm_unique_id and ships the 128 bytes to the other ranks (the launcher's store, MPI or a file);
    every rank then calls xsb_comm_init BEFORE xsb_assemble.  nranks = 1 is a no-op. */
 int xsb_comm_unique_id(void *out128);
+/* out[0]=rank [1]=nranks [2]=1 when ghost planes travel through the peer-memory exchange kernel (0: ncclSend/ncclRecv)
+   [3]=bit l set when MG level l is distributed by node planes (after xsb_ksp_setup) */
+int xsb_comm_info(xsb_ctx ctx, int64_t out[4]);
 int xsb_comm_init(xsb_ctx ctx, const void *unique_id, int rank, int nranks);
 /* partition of this rank after xsb_assemble: out[0]=rank [1]=nranks [2..3]=owned element layers [k0,k1)
    [4..5]=local lattice layers [e0,e1) [6]=offset,[7]=length of the owned velocity entries in a local vector

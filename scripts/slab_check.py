@@ -60,7 +60,11 @@ for name, opts, ptype in (("jacobi_gmres", "-model 1 -mx %d -eta1 10 -saddle_pc_
                           ("abf_bjacobi_ilu", ABF + "-saddle_fieldsplit_p_pc_type bjacobi -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf_ilu"),
                           ("abf_pjacobi_mf", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_matrix_free -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
                           ("abf_pjacobi_mffull", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_matrix_free full -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
-                          ("abf_pjacobi_rowpart", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_rowpart_min_nodes 100 -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf")):
+                          # coarse levels distributed by node planes: level 1 of 3 (gathers into the replicated coarsest level), levels 2 and 1 of 4
+                          ("abf_pjacobi_pdist3", ABF + "-saddle_fieldsplit_p_pc_type jacobi -xsb_pdist_min_nodes 1 -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
+                          ("abf_pjacobi_pdist4_mffull", ABF + "-saddle_fieldsplit_u_pc_mg_levels 4 -saddle_fieldsplit_p_pc_type jacobi -xsb_pdist_min_nodes 1 -xsb_matrix_free full -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf"),
+                          # the same with ncclSend / ncclRecv instead of the peer-memory exchange kernel
+                          ("abf_pjacobi_pdist4_nccl", ABF + "-saddle_fieldsplit_u_pc_mg_levels 4 -saddle_fieldsplit_p_pc_type jacobi -xsb_pdist_min_nodes 1 -xsb_p2p 0 -model 6 -mx %d -eta1 100 -saddle_ksp_rtol 1e-8" % MX, "abf")):
     gd = make(opts, True)
     part = gd.partition()
     g1 = make(opts, False)          # every rank keeps a one-GPU copy as the reference (small problem)

@@ -158,6 +158,33 @@ def test_vcycle_ilu_and_fieldsplit_apply(abf_pair):
     assert np.linalg.norm(zg - zo) <= 1e-8 * np.linalg.norm(zo)
 
 
+@pytest.mark.parametrize("nsd,levels,opts", [(3, 1, "-model 6 -mx 5 -my 3 -mz 4 -eta1 1e4"), (3, 1, "-model 1 -mx 2 -my 6 -mz 9 -eta1 10"), (3, 3, "-model 6 -mx 16 -eta1 1e6"),
+                                             (3, 1, "-model 2 -mx 1"), (2, 1, "-model 6 -mx 9 -my 4 -eta1 100"), (3, 3, "-model 6 -mx 40 -my 32 -mz 8 -eta1 1e3")])
+def test_pressure_ilu0_solve_pipelined_vs_wavefront_vs_oracle(nsd, levels, opts):
+    """bjacobi/ILU(0) on Mpscaled (abf.opts:15): the line-pipelined triangular solve (default) against the oracle's sequential
+    MatSolve (<= 1e-12) and, bit for bit, against the wavefront kernel it replaces (-xsb_ilu_kernel 0); twice, because the
+    step counters the CTAs hand to each other must be back at zero after a launch."""
+    abf = ABF + " -saddle_fieldsplit_u_pc_mg_levels %d" % levels
+    o = O.Problem(opts, nsd=nsd)
+    M = o.Mp(); lu = np.empty_like(M.a)
+    assert O.lib().xo_ilu0(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
+    rng = np.random.default_rng(3)
+    out = {}
+    for kern in (1, 0):
+        g = X.ExSaddle(abf + " " + opts + " -xsb_ilu_kernel %d" % kern, nsd=nsd).assemble().ksp_setup()
+        res = []
+        for rep in range(2):
+            bp = np.cos(0.3 * np.arange(o.np_) + rep)
+            xp = np.empty(o.np_); O.lib().xo_ilu0_solve(o.np_, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(bp), O._dp(xp))
+            xg = g.pc_schur_apply(bp)
+            assert np.linalg.norm(xg - xp) <= 1e-12 * np.linalg.norm(xp), (kern, rep)
+            res.append(xg)
+        out[kern] = res
+        g.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_abf_solve_history_matches_oracle(abf_pair):
     g, o, res, levels = abf_pair
     x = g.solve()

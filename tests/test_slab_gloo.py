@@ -70,18 +70,39 @@ def _worker(rank, world, port, mx, my, mz, q):
         for z in range(zp0, zp1 + 1):
             zl = z - lay["e0"]
             assert np.array_equal(loc[nu_loc + zl * pp: nu_loc + (zl + 1) * pp], xg[nu_g + z * pp: nu_g + (z + 1) * pp]), ("p plane", z)
-        # 4. replay comm_allgather_planes (row-partitioned product on a replicated coarse level): nz planes, equal chunks of
-        #    cp = ceil(nz / N) planes, the vector padded to N cp planes, rank r fills [r cp, min((r+1) cp, nz))
-        for nz, pd in ((mz + 1, 7), (2 * mz + 1, 5)):
-            cp = -(-nz // world)
-            want = np.cos(0.11 * np.arange(nz * pd))
-            buf = np.full(world * cp * pd, -1.0)
-            r0, r1 = min(rank * cp, nz), min((rank + 1) * cp, nz)
-            buf[r0 * pd:r1 * pd] = want[r0 * pd:r1 * pd]
-            parts = [torch.empty(cp * pd, dtype=torch.float64) for _ in range(world)]
-            dist.all_gather(parts, torch.from_numpy(buf[rank * cp * pd:(rank + 1) * cp * pd].copy()))
-            got = torch.cat(parts).numpy()
-            assert np.array_equal(got[:nz * pd], want), ("all-gather of equal padded chunks", nz)
+        # 4. replay the plane-distributed coarse levels (Level::pdist): ownership from xsb_pdist_range, products exchange their
+        #    OUTPUT planes (one below, one above), restriction to the next level needs nothing further, and the gather into a
+        #    replicated level is one broadcast per rank of the planes it restricted
+        for depth in range(0, 3):
+            rng = [X.pdist_range(mz, world, r, depth) for r in range(world)]
+            if mz % (1 << depth) or min(b - a for a, b in rng) < 1:
+                break
+            nzl = mz // (1 << depth) + 1
+            assert rng[0][0] == 0 and rng[-1][1] == nzl and all(rng[r][1] == rng[r + 1][0] for r in range(world - 1)), ("ranges tile the level", depth, rng)
+            p0, p1 = rng[rank]; pd = 5
+            want = np.sin(0.13 * np.arange(nzl * pd) + depth)
+            v = np.full(nzl * pd, np.nan); v[p0 * pd:p1 * pd] = want[p0 * pd:p1 * pd]          # "product": owned rows only
+            ops = []; ghosts = []
+            if rank > 0:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(v[p0 * pd:(p0 + 1) * pd].copy()), rank - 1)); gb = torch.empty(pd, dtype=torch.float64); ops.append(dist.P2POp(dist.irecv, gb, rank - 1)); ghosts.append((p0 - 1, gb))
+            if rank < world - 1:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(v[(p1 - 1) * pd:p1 * pd].copy()), rank + 1)); ga = torch.empty(pd, dtype=torch.float64); ops.append(dist.P2POp(dist.irecv, ga, rank + 1)); ghosts.append((p1, ga))
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+            for z, t in ghosts:
+                v[z * pd:(z + 1) * pd] = t.numpy()
+            lo, hi = max(p0 - 1, 0), min(p1 + 1, nzl)
+            assert np.array_equal(v[lo * pd:hi * pd], want[lo * pd:hi * pd]), ("planes current after the exchange", depth)
+            # restriction stencil of the owned coarse planes stays inside the current planes
+            K0, K1 = (p0 + 1) // 2, (p1 + 1) // 2
+            assert (K0, K1) == X.pdist_range(mz, world, rank, depth + 1)
+            for K in range(K0, K1):
+                for z in range(max(2 * K - 1, 0), min(2 * K + 1, nzl - 1) + 1):
+                    assert lo <= z < hi, ("restriction reads current planes", depth, K, z)
+            # prolongation of the owned planes and of the two neighbour planes reads coarse planes [K0-1, K1]
+            for z in range(lo, hi):
+                for cz in ((z // 2,) if z % 2 == 0 else (z // 2, z // 2 + 1)):
+                    assert K0 - 1 <= cz <= K1, ("prolongation reads current coarse planes", depth, z)
         dist.barrier(); dist.destroy_process_group()
         q.put((rank, "ok"))
     except Exception as e:   # report instead of hanging the parent
