@@ -49,7 +49,7 @@ def lib():
             "xsb_vec_get_rhs": [vp, dp], "xsb_get_bc": [vp, i32p, dp], "xsb_get_coeff_qp": [vp, C.c_int, dp],
             "xsb_ksp_setup": [vp], "xsb_ksp_reset": [vp], "xsb_get_state": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)], "xsb_ksp_solve": [vp, dp, dp], "xsb_ksp_solve_dev": [vp, vp, vp],
             "xsb_pc_apply": [vp, dp, dp], "xsb_pc_apply_dev": [vp, vp, vp], "xsb_pc_mg_apply": [vp, dp, dp],
-            "xsb_pc_schur_apply": [vp, dp, dp], "xsb_time_pc_schur": [vp, C.c_int, dp], "xsb_mg_restrict": [vp, C.c_int, dp, dp],
+            "xsb_pc_schur_apply": [vp, dp, dp], "xsb_time_pc_schur": [vp, C.c_int, dp], "xsb_time_halo": [vp, C.c_int, dp], "xsb_mg_restrict": [vp, C.c_int, dp, dp],
             "xsb_mg_interpolate_add": [vp, C.c_int, dp, dp],
             "xsb_ksp_get_iterations": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "xsb_ksp_get_history": [vp, dp, C.c_int, C.POINTER(C.c_int)],
@@ -278,6 +278,10 @@ class ExSaddle:
     def time_pc_schur(self, reps=20):
         ms = C.c_double()
         self._chk(self.L.xsb_time_pc_schur(self.h, reps, C.byref(ms))); return ms.value
+
+    def time_halo(self, reps=50):
+        out = (C.c_double * 3)()
+        self._chk(self.L.xsb_time_halo(self.h, reps, out)); return {"halo_u_us": out[0], "halo_plane_us": out[1], "a00_kernel_us": out[2]}
 
     def pc_schur_apply(self, b):
         b = np.ascontiguousarray(b, dtype=np.float64); x = np.empty(self.np_)

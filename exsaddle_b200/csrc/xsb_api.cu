@@ -380,6 +380,31 @@ int xsb_pc_schur_apply(xsb_ctx c, const double *b, double *x)
     return vec_pmult(cc, cc->lat.np, cc->mp_idiag, a, bb); });
 }
 
+// device time (us) of `reps` back-to-back ghost exchanges of a velocity vector (collective), and of the fine-level A00 kernel
+// without its exchange: out[0] = exchange, out[1] = exchange of a single node plane per side (a distributed coarse level),
+// out[2] = fine-level product without exchange
+int xsb_time_halo(xsb_ctx c, int reps, double out[3])
+{
+  NEED_DEVICE(c);
+  if (!c->ksp_ready || reps < 1 || !out) return xsb_fail(c, XSB_ERR_ORDER, "solver not set up");
+  const Lattice &L = c->lat; double *a = c->w_t1, *bb = c->w_t2; float ms = 0;
+  XSB_CHK(vec_set(c, L.n, 1.0, a));
+  for (int which = 0; which < 3; ++which) {
+    auto one = [&]() -> int {
+      if (which == 0) return comm_halo_u(c, a);
+      if (which == 1) return comm_halo_planes(c, a, (int64_t)L.nsd * (L.mx + 1) * (L.my + 1), c->slab.ou0, c->slab.ou1, 1, 1);
+      Epilogue ep; if (c->so.matrix_free) return mf_a00_apply(c, a, bb, ep);
+      const int pn = L.NX * L.NY; return spmv_baij(c, c->A00, a, bb, ep, c->slab.ou0 * pn, (c->slab.ou1 - c->slab.ou0) * pn); };
+    XSB_CHK(one()); XSB_CHK(one());
+    CUDA_OK(cudaEventRecord(c->evk0, c->stream));
+    for (int i = 0; i < reps; ++i) XSB_CHK(one());
+    CUDA_OK(cudaEventRecord(c->evk1, c->stream)); CUDA_OK(cudaEventSynchronize(c->evk1));
+    CUDA_OK(cudaEventElapsedTime(&ms, c->evk0, c->evk1));
+    out[which] = 1e3 * (double)ms / reps;
+  }
+  return XSB_OK;
+}
+
 // device time of `reps` pressure-block solves (ILU(0) or Jacobi) on resident vectors, CUDA events on the handle's stream
 int xsb_time_pc_schur(xsb_ctx c, int reps, double *ms_per_apply)
 {

@@ -84,66 +84,64 @@ int comm_allreduce_sum(xsb_ctx c, double *dev, int n)
 }
 
 // ------------------------------------------------------------------ peer-memory halo exchange (NVLink / NVSwitch)
-// ncclSend/ncclRecv of a ghost plane costs ~50 us per exchange (measured: fine-level product 164 us at N = 2 against 95 us of
-// arithmetic), and the solve does one in front of every operator product -- far more than the 0.4 - 3 MB of a plane need on
-// NVLink.  So the exchange is ONE kernel over peer memory: every rank owns a small window (cudaMalloc, opened by both
-// neighbours through cudaIpc handles exchanged once with ncclAllGather); the kernel
-//   A. copies this rank's boundary planes straight into the neighbours' windows (stores over NVLink), fences, and the last
-//      block to finish stores the exchange's sequence number into the neighbours' flag words (st.release.sys);
-//   B. waits (ld.acquire.sys) until both neighbours' sequence numbers have arrived in its OWN flag words, then copies the
-//      window slots into the ghost planes of the vector.
-// Windows are double-buffered by the parity of the sequence number: a rank can only start exchange s+2 after it finished
-// part B of s+1, i.e. after the neighbour finished part A of s+1, which is stream-ordered behind the neighbour's whole kernel s
-// -- so slot s%2 is free again, without acknowledgements.  The sequence number lives in device memory (read and advanced by
-// the kernel), so the kernel replays correctly inside CUDA graphs.  A wait that exceeds ~2 s (a neighbour died) raises a
-// sticky error word instead of hanging the GPU; xsb_ksp_solve reports it.
+// The solve exchanges ghost planes in front of every fine-level product and behind every product of a distributed coarse
+// level (~3300 exchanges per 128^3 solve), 0.4 - 3 MB each: latency, not bandwidth.  ncclSend/ncclRecv cost 15 - 22 us per
+// exchange here; so did a first peer-memory kernel that published a sequence number behind system-scope fences.  The
+// exchange is now ONE kernel without fences or flags -- THE VALUE IS THE FLAG (the idea of NCCL's LL protocol, for doubles):
+//   * every rank owns a window (cudaMalloc, opened by both neighbours through cudaIpc handles exchanged once with
+//     ncclAllGather), two slots per direction, kept filled with a sentinel (a quiet NaN whose payload no computation produces);
+//   A. the kernel stores this rank's boundary planes straight into the neighbours' windows (plain 8-byte stores over NVLink);
+//   B. each thread then reads its share of the rank's OWN window, re-reading an element until it is no longer the sentinel
+//      (an 8-byte store is single-copy atomic, and nothing but the value itself is awaited), copies it into the ghost
+//      plane and puts the sentinel back.
+// Slots alternate with the parity of an exchange counter in device memory (advanced by the last block, so the kernel replays
+// inside CUDA graphs).  Slot s%2 is free again when a rank starts exchange s+2: it has finished part B of s+1, so the
+// neighbour finished part A of s+1, which is stream-ordered behind the neighbour's whole kernel s (its reads and its
+// sentinel stores).  A wait beyond ~2 s (a neighbour died) raises a sticky error word instead of hanging the GPU.
 struct P2P {
   bool on = false;
   char *win = nullptr, *peer_lo = nullptr, *peer_hi = nullptr;   // my window, the windows of rank-1 / rank+1
-  unsigned long long *ctl = nullptr;                               // local control words: [0] sequence, [1] part-A blocks done, [2] error, [3] part-B blocks done
+  unsigned long long *ctl = nullptr;                               // local control words: [0] exchange counter, [1] blocks done, [2] error
   size_t slot_bytes = 0;
 };
-enum { P2P_HDR = 256 };   // window: [flag from below, flag from above, pad][from-below slot 0,1][from-above slot 0,1]
+enum { P2P_HDR = 256 };   // window: [pad][from-below slot 0,1][from-above slot 0,1]
+#define P2P_SENTINEL 0x7FF8C0FFEE5EED01ULL
 struct P2PDev { unsigned long long *ctl; char *win, *peer_lo, *peer_hi; size_t slot_bytes; };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{ unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{ asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p)
+{ unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__global__ void k_p2p_fill(unsigned long long *w, size_t n) { for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) w[i] = P2P_SENTINEL; }
 
 __global__ void __launch_bounds__(256) k_halo_p2p(double *__restrict__ v, int64_t pd, int o0, int o1, int gb, int ga, P2PDev w)
 {
-  __shared__ unsigned long long s_seq; __shared__ int s_err;
+  __shared__ unsigned long long s_seq;
   const bool lo = w.peer_lo != nullptr, hi = w.peer_hi != nullptr;
-  if (threadIdx.x == 0) { s_seq = *(volatile unsigned long long *)&w.ctl[0] + 1; s_err = (int)*(volatile unsigned long long *)&w.ctl[2]; }
+  if (threadIdx.x == 0) s_seq = *(volatile unsigned long long *)&w.ctl[0];
   __syncthreads();
-  const unsigned long long seq = s_seq; const int slot = (int)(seq & 1);
+  const int slot = (int)(s_seq & 1);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   // A: my bottom `ga` owned planes are the neighbour below's ghost planes above; my top `gb` owned planes the ghosts below of the neighbour above
   if (lo) { double *dst = (double *)(w.peer_lo + P2P_HDR + (size_t)(2 + slot) * w.slot_bytes); const double *src = v + (int64_t)o0 * pd; for (int64_t i = tid; i < ga * pd; i += nth) dst[i] = src[i]; }
   if (hi) { double *dst = (double *)(w.peer_hi + P2P_HDR + (size_t)(0 + slot) * w.slot_bytes); const double *src = v + (int64_t)(o1 - gb) * pd; for (int64_t i = tid; i < gb * pd; i += nth) dst[i] = src[i]; }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (atomicAdd(&w.ctl[1], 1ULL) == gridDim.x - 1) {   // every block's planes are on their way: publish
-      w.ctl[1] = 0; __threadfence_system();
-      if (lo) st_release_sys((unsigned long long *)w.peer_lo + 1, seq);   // I am the rank ABOVE rank-1
-      if (hi) st_release_sys((unsigned long long *)w.peer_hi + 0, seq);
-    }
-    // B: wait for both neighbours' planes of this exchange
-    if (!s_err) {
-      const long long t0 = clock64(); const unsigned long long *fl = (const unsigned long long *)w.win;
-      while ((lo && ld_acquire_sys(fl + 0) < seq) || (hi && ld_acquire_sys(fl + 1) < seq)) {
-        if (clock64() - t0 > 4000000000LL) { atomicExch(&w.ctl[2], 1ULL); break; }
-        __nanosleep(100);
+  // B: my ghost planes from my own window
+  bool dead = *(volatile unsigned long long *)&w.ctl[2] != 0;
+  for (int side = 0; side < 2; ++side) {
+    if (side == 0 ? !lo : !hi) continue;
+    unsigned long long *src = (unsigned long long *)(w.win + P2P_HDR + (size_t)((side ? 2 : 0) + slot) * w.slot_bytes);
+    double *dst = side ? v + (int64_t)o1 * pd : v + (int64_t)(o0 - gb) * pd;
+    const int64_t n = (side ? ga : gb) * pd;
+    for (int64_t i = tid; i < n; i += nth) {
+      unsigned long long x = ld_relaxed_sys_u64(src + i);
+      if (x == P2P_SENTINEL && !dead) {
+        const long long t0 = clock64();
+        do { x = ld_relaxed_sys_u64(src + i); if (clock64() - t0 > 4000000000LL) { atomicExch(&w.ctl[2], 1ULL); dead = true; break; } } while (x == P2P_SENTINEL);
       }
+      dst[i] = __longlong_as_double((long long)x);
+      src[i] = P2P_SENTINEL;
     }
   }
   __syncthreads();
-  if (lo) { const double *src = (const double *)(w.win + P2P_HDR + (size_t)(0 + slot) * w.slot_bytes); double *dst = v + (int64_t)(o0 - gb) * pd; for (int64_t i = tid; i < gb * pd; i += nth) dst[i] = __ldcg(src + i); }
-  if (hi) { const double *src = (const double *)(w.win + P2P_HDR + (size_t)(2 + slot) * w.slot_bytes); double *dst = v + (int64_t)o1 * pd; for (int64_t i = tid; i < ga * pd; i += nth) dst[i] = __ldcg(src + i); }
-  __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(&w.ctl[3], 1ULL) == gridDim.x - 1) { w.ctl[3] = 0; *(volatile unsigned long long *)&w.ctl[0] = seq; }   // the last block closes the exchange
+  if (threadIdx.x == 0 && atomicAdd(&w.ctl[1], 1ULL) == gridDim.x - 1) { w.ctl[1] = 0; *(volatile unsigned long long *)&w.ctl[0] = s_seq + 1; }   // the last block closes the exchange
 }
 
 static void p2p_release(xsb_ctx c, bool collective)
@@ -170,12 +168,13 @@ int comm_p2p_setup(xsb_ctx c)
   if (p && p->on && p->slot_bytes == need) return 0;   // NX, NY are global: every rank takes the same branch
   p2p_release(c, true);
   p = new P2P(); c->p2p = p; p->slot_bytes = need;
-  CUDA_OK(cudaMalloc(&p->win, P2P_HDR + 4 * need)); CUDA_OK(cudaMemsetAsync(p->win, 0, P2P_HDR + 4 * need, c->stream));
+  CUDA_OK(cudaMalloc(&p->win, P2P_HDR + 4 * need)); CUDA_OK(cudaMemsetAsync(p->win, 0, P2P_HDR, c->stream));
+  k_p2p_fill<<<256, 256, 0, c->stream>>>((unsigned long long *)(p->win + P2P_HDR), 4 * need / 8); KERNEL_OK();
   CUDA_OK(cudaMalloc(&p->ctl, 64)); CUDA_OK(cudaMemsetAsync(p->ctl, 0, 64, c->stream));
   cudaIpcMemHandle_t mine; CUDA_OK(cudaIpcGetMemHandle(&mine, p->win));
   char *hd = nullptr; CUDA_OK(cudaMalloc(&hd, sizeof(mine) * S.nranks));
   CUDA_OK(cudaMemcpyAsync(hd + sizeof(mine) * S.rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
-  NCCL_OK(g_nccl.AllGather(hd + sizeof(mine) * S.rank, hd, sizeof(mine), 0 /* ncclInt8 */, (ncclComm_t)c->nccl, c->stream));   // also orders every rank's memset before anyone's first push
+  NCCL_OK(g_nccl.AllGather(hd + sizeof(mine) * S.rank, hd, sizeof(mine), 0 /* ncclInt8 */, (ncclComm_t)c->nccl, c->stream));   // also orders every rank's sentinel fill before anyone's first push
   std::vector<cudaIpcMemHandle_t> all(S.nranks);
   CUDA_OK(cudaMemcpyAsync(all.data(), hd, sizeof(mine) * S.nranks, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaFree(hd));
@@ -212,7 +211,7 @@ int comm_halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb, i
   const P2P *p = (const P2P *)c->p2p;
   if (p && p->on && (size_t)((gb > ga ? gb : ga) * pd) * sizeof(double) <= p->slot_bytes) {
     P2PDev w{p->ctl, p->win, p->peer_lo, p->peer_hi, p->slot_bytes};
-    int64_t blocks = ((gb > ga ? gb : ga) * pd + 2047) / 2048; if (blocks > 64) blocks = 64; if (blocks < 1) blocks = 1;
+    int64_t blocks = ((gb > ga ? gb : ga) * pd + 1023) / 1024; if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
     k_halo_p2p<<<(unsigned)blocks, 256, 0, c->stream>>>(v, pd, o0, o1, gb, ga, w); KERNEL_OK();
     return 0;
   }

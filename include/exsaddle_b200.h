@@ -103,6 +103,9 @@ int xsb_pc_mg_apply(xsb_ctx ctx, const double *b, double *x);     /* PCApply_MG 
 int xsb_pc_schur_apply(xsb_ctx ctx, const double *b, double *x);  /* fieldsplit_p PC on Mpscaled, host pointers */
 /* measurement aid: average device time (ms) of `reps` pressure-block solves on resident vectors */
 int xsb_time_pc_schur(xsb_ctx ctx, int reps, double *ms_per_apply);
+/* measurement aid (collective on slabs): average device time in us of [0] a velocity ghost exchange, [1] a one-plane exchange
+   (distributed coarse level), [2] a fine-level A00 product without its exchange */
+int xsb_time_halo(xsb_ctx ctx, int reps, double out[3]);
 int xsb_mg_restrict(xsb_ctx ctx, int coarse_level, const double *rf, double *bc);     /* MatRestrict */
 int xsb_mg_interpolate_add(xsb_ctx ctx, int coarse_level, const double *xc, double *xf); /* MatInterpolateAdd */
 
