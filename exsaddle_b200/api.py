@@ -62,6 +62,8 @@ def lib():
             "xsb_prealloc_total": [C.c_int, C.c_int, C.c_int, C.c_int],
             "xsb_bc_list": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int],
             "xsb_mg_level_dims": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
+            "xsb_dmda_grid": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
+            "xsb_asm_subdomain": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
             "xsb_slab_range": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "xsb_pdist_range": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "xsb_slab_layout": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64p],
@@ -123,6 +125,25 @@ def slab_range(mz, nranks, rank):
     if rc:
         raise XsbError(rc, "bad slab request")
     return a.value, b.value
+
+
+def dmda_grid(nsd, M, N, P, size):
+    """process grid of DMDACreate{2,3}d with PETSC_DECIDE (xsb_dmda_grid)"""
+    out = (C.c_int * 3)()
+    rc = lib().xsb_dmda_grid(nsd, M, N, P, size, out)
+    if rc:
+        raise XsbError(rc, "no process grid")
+    return tuple(out)
+
+
+def asm_subdomain(nsd, mx, my, mz, size, overlap, rank):
+    """element patch and owned node ranges of one rank's ASM subdomain (xsb_asm_subdomain)"""
+    out = (C.c_int * 18)()
+    rc = lib().xsb_asm_subdomain(nsd, mx, my, mz, size, overlap, rank, out)
+    if rc:
+        raise XsbError(rc, "Cannot generate consistent macro element")
+    v = list(out)
+    return {"lo": v[0:nsd], "hi": v[3:3 + nsd], "own_u": [(v[6 + d], v[9 + d]) for d in range(nsd)], "own_p": [(v[12 + d], v[15 + d]) for d in range(nsd)]}
 
 
 def pdist_range(mz, nranks, rank, depth):

@@ -144,7 +144,7 @@ struct Model {   // resolved model parameters (models.c static option blocks)
 
 struct SolverOpts {
   int ksp_type = 0;      // 0 gmres 1 fgmres
-  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf) 3 monolithic PCMG (-mg) 4 fieldsplit with PETSc's default sub-solvers (plain -fs)
+  int pc_type = 0;       // 0 none 1 jacobi 2 fieldsplit (abf) 3 monolithic PCMG (-mg) 4 fieldsplit with PETSc's default sub-solvers (plain -fs) 5 ASM on element patches
   int right = 0;
   double rtol = 1e-5, atol = 1e-50, dtol = 1e4; int max_it = 10000, restart = 30;
   double u_rtol = 1e-5; int u_max_it = 10000, u_restart = 30;
@@ -214,6 +214,7 @@ struct xsb_ctx_s {
   std::vector<char> alloc_phase; int phase = 0;   // 0: xsb_assemble, 1: xsb_ksp_setup (freed when the solver is set up again), 2: lazily created element-kernel state
   void *fe_tables = nullptr;    // FeTables on the device
   void *mmg = nullptr;          // monolithic -mg hierarchy (xsb_mmg.cu)
+  void *asmpc = nullptr;        // -saddle_pc_type asm (xsb_asm.cu)
   void *fsd = nullptr;          // default -fs tree: GMRES + ILU(0) sub-solvers (xsb_fs.cu)
   const double *nodal_in = nullptr;   // coarse -mg level: nodal Q1 coefficient fields [slot][p-node] to use instead of the model
 };
@@ -299,6 +300,11 @@ int mg_prolong_add_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny
 int mmg_setup(xsb_ctx c);
 int mmg_apply(xsb_ctx c, const double *r, double *z);
 void mmg_free(xsb_ctx c);
+// ---- xsb_asm.cu (additive Schwarz on the reference's element patches)
+int asm_setup(xsb_ctx alloc, xsb_ctx problem, int size, int overlap, void **out);
+int asm_apply(xsb_ctx c, void *asmpc, const double *r, double *z);
+void asm_free(void *asmpc);
+int dense_invert_pivoted(xsb_ctx c, int n, double *M, double *Inv);
 // ---- xsb_fs.cu (plain -fs tree with PETSc's default sub-solvers)
 int fsd_setup(xsb_ctx c);
 int fsd_apply(xsb_ctx c, const double *r, double *z);

@@ -123,6 +123,7 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reaso
   if (c->so.pc_type == 0) return vec_copy(c, L.n, r, z);
   if (c->so.pc_type == 3) return mmg_apply(c, r, z);
   if (c->so.pc_type == 4) return fsd_apply(c, r, z);
+  if (c->so.pc_type == 5) return asm_apply(c, c->asmpc, r, z);
   // PCApply_FieldSplit_Schur, PC_FIELDSPLIT_SCHUR_FACT_UPPER
   double *yp = z + L.nu;
   XSB_CHK(prof_mark(c, PROF_ILU));
@@ -150,6 +151,7 @@ static int read_solver_options(xsb_ctx c)
   if (fs && mg) return xsb_fail(c, XSB_ERR_SUP, "both -fs and -mg supplied");              // exSaddle.c:205
   if (o.integer("nlevels", 1) > 1 && fs) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified with -fs");      // exSaddle.c:207
   if (o.integer("nlevels", 1) > 1 && !mg) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified without -mg"); // exSaddle.c:208
+  if (o.flag("set_ksp_dm") && (mg || fs)) return xsb_fail(c, XSB_ERR_SUP, "-set_ksp_dm not intended for use with -mg or -fs");   // exSaddle.c:212
   if (mg) {
     s.pc_type = 3;   // monolithic PCMG on the saddle operator (xsb_mmg.cu)
     if (o.flag("fs_coarse")) return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse (fieldsplit coarse solver) is not implemented");
@@ -169,7 +171,15 @@ static int read_solver_options(xsb_ctx c)
     if (!o.has("saddle_pc_type")) return xsb_fail(c, XSB_ERR_SUP, "no -saddle_pc_type given: PETSc's default (ilu / bjacobi+ilu on the saddle matrix) is not implemented; pass -saddle_pc_type jacobi|none, -fs or -mg");
     const std::string pc = o.str("saddle_pc_type", "none");
     if (pc == "jacobi") s.pc_type = 1; else if (pc == "none") s.pc_type = 0;
-    else return xsb_fail(c, XSB_ERR_SUP, "-saddle_pc_type %s not supported without -fs (jacobi|none)", pc.c_str());
+    else if (pc == "asm") {
+      // Makefile:298, 411: one element patch per rank (DMCreateDomainDecomposition of the KSP's DM) with exact sub-solves.  Without
+      // -saddle_pc_asm_dm_subdomains / -set_ksp_dm PETSc would cut subdomains from the matrix graph instead: not implemented.
+      s.pc_type = 5;
+      if (!o.flag("saddle_pc_asm_dm_subdomains") || !o.flag("set_ksp_dm")) return xsb_fail(c, XSB_ERR_SUP, "-saddle_pc_type asm is supported on the reference's element patches: add -saddle_pc_asm_dm_subdomains -set_ksp_dm");
+      if (o.str("saddle_sub_pc_type", "ilu") != "lu" || o.str("saddle_sub_ksp_type", "preonly") != "preonly") return xsb_fail(c, XSB_ERR_SUP, "ASM sub-solves: -saddle_sub_ksp_type preonly -saddle_sub_pc_type lu");
+      o.has("saddle_sub_pc_factor_mat_solver_type"); o.has("dmdafe_overlap"); o.has("xsb_ranks");
+    }
+    else return xsb_fail(c, XSB_ERR_SUP, "-saddle_pc_type %s not supported without -fs (jacobi|none|asm)", pc.c_str());
   }
   s.right = (o.str("saddle_ksp_pc_side", ksp == "fgmres" ? "right" : "left") == "right") || s.ksp_type == 1;
   s.rtol = o.real("saddle_ksp_rtol", 1e-5); s.atol = o.real("saddle_ksp_atol", 1e-50); s.dtol = o.real("saddle_ksp_divtol", 1e4);
@@ -222,6 +232,7 @@ int ksp_release(xsb_ctx c)
   CUDA_OK(cudaStreamSynchronize(c->stream));
   mg_graphs_release(c);
   mmg_free(c); fsd_free(c);
+  if (c->asmpc) { asm_free(c->asmpc); c->asmpc = nullptr; }
   dev_free_phase(c, 1);
   c->red = c->scal = nullptr; c->w_t1 = c->w_t2 = c->xdev = c->bdev = c->idiagA = c->gcr_r = c->fs_tu = nullptr;
   c->mp_lu = c->mp_idiag = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
@@ -249,6 +260,7 @@ int ksp_setup(xsb_ctx c)
   if (c->so.pc_type == 1) { XSB_CHK(dev_alloc(c, &c->idiagA, (size_t)L.n)); XSB_CHK(csr_diag_inv(c, c->A, c->idiagA)); }
   if (c->so.pc_type == 3) XSB_CHK(mmg_setup(c));
   if (c->so.pc_type == 4) XSB_CHK(fsd_setup(c));
+  if (c->so.pc_type == 5) XSB_CHK(asm_setup(c, c, c->opt.integer("xsb_ranks", 1), c->opt.integer("dmdafe_overlap", 0), &c->asmpc));
   if (c->so.pc_type == 2) {
     if (c->so.matrix_free) XSB_CHK(mf_setup(c));
     XSB_CHK(mg_setup(c));

@@ -22,6 +22,7 @@ struct MmgLevel {
   double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
   std::vector<double *> V;    // GMRES basis of the smoother
   double *inv = nullptr;      // coarsest: dense inverse
+  void *asmpc = nullptr;      // -saddle_mg_levels_pc_type asm: element-patch ASM instead of Jacobi (xsb_asm.cu)
 };
 struct Mmg { int nlev = 0, smooth_its = 2, restart = 30; std::vector<MmgLevel> lev; };
 
@@ -99,14 +100,15 @@ __global__ void k_gemv_rows(int n, const double *__restrict__ M, const double *_
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) x[row] = acc;
 }
-static int dense_inverse_pivoted(xsb_ctx c, const Csr &A, double **inv_out)
+// Inv = M^-1 for a dense n x n matrix M (row-major, destroyed): Gauss-Jordan on [M | I] with partial pivoting
+int dense_invert_pivoted(xsb_ctx c, int n, double *M, double *Inv)
 {
-  const int n = A.n; cudaStream_t st = c->stream;
-  if (n > 6600) return xsb_fail(c, XSB_ERR_SUP, "coarsest -mg level has %d unknowns; the dense coarse solve supports <= 6600 (use more -nlevels)", n);
-  double *M = nullptr, *Inv = nullptr, *colk = nullptr, *pval = nullptr; int *piv = nullptr, *flag = nullptr;
-  XSB_CHK(dev_alloc(c, &Inv, (size_t)n * n)); XSB_CHK(dev_alloc(c, &colk, (size_t)n)); XSB_CHK(dev_alloc(c, &pval, 1)); XSB_CHK(dev_alloc(c, &piv, 1)); XSB_CHK(dev_alloc(c, &flag, 1));
-  CUDA_OK(cudaMalloc(&M, sizeof(double) * (size_t)n * n)); CUDA_OK(cudaMemsetAsync(M, 0, sizeof(double) * (size_t)n * n, st));
-  k_csr_to_dense<<<nblk(n), 256, 0, st>>>(n, A.ia, A.ja, A.a, M); KERNEL_OK();
+  cudaStream_t st = c->stream;
+  double *colk = nullptr, *pval = nullptr; int *piv = nullptr, *flag = nullptr;
+  CUDA_OK(cudaMalloc(&colk, sizeof(double) * ((size_t)n + 2))); pval = colk + n;
+  CUDA_OK(cudaMalloc(&piv, sizeof(int) * 2)); flag = piv + 1;
+  CUDA_OK(cudaMemsetAsync(piv, 0, sizeof(int) * 2, st));
+  CUDA_OK(cudaMemsetAsync(Inv, 0, sizeof(double) * (size_t)n * n, st));
   k_identity<<<nblk(n), 256, 0, st>>>(n, Inv); KERNEL_OK();
   dim3 g2((n + 255) / 256, n);
   for (int k = 0; k < n; ++k) {
@@ -116,8 +118,21 @@ static int dense_inverse_pivoted(xsb_ctx c, const Csr &A, double **inv_out)
     k_gjp_eliminate<<<g2, 256, 0, st>>>(n, k, M, Inv, colk); KERNEL_OK();
   }
   int hflag = 0; CUDA_OK(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); CUDA_OK(cudaStreamSynchronize(st));
-  CUDA_OK(cudaFree(M));
-  if (hflag) return xsb_fail(c, XSB_ERR_BREAKDOWN, "singular coarse saddle matrix in the -mg coarse solve");
+  cudaFree(colk); cudaFree(piv);
+  if (hflag) return xsb_fail(c, XSB_ERR_BREAKDOWN, "singular matrix in a dense direct solve (-mg coarse level / ASM subdomain)");
+  return 0;
+}
+static int dense_inverse_pivoted(xsb_ctx c, const Csr &A, double **inv_out)
+{
+  const int n = A.n; cudaStream_t st = c->stream;
+  if (n > 6600) return xsb_fail(c, XSB_ERR_SUP, "coarsest -mg level has %d unknowns; the dense coarse solve supports <= 6600 (use more -nlevels)", n);
+  double *M = nullptr, *Inv = nullptr;
+  XSB_CHK(dev_alloc(c, &Inv, (size_t)n * n));
+  CUDA_OK(cudaMalloc(&M, sizeof(double) * (size_t)n * n)); CUDA_OK(cudaMemsetAsync(M, 0, sizeof(double) * (size_t)n * n, st));
+  k_csr_to_dense<<<nblk(n), 256, 0, st>>>(n, A.ia, A.ja, A.a, M); KERNEL_OK();
+  int rc = dense_invert_pivoted(c, n, M, Inv);
+  cudaFree(M);
+  if (rc) return rc;
   *inv_out = Inv;
   return 0;
 }
@@ -139,6 +154,10 @@ static int mmg_prolong_add(xsb_ctx c, const MmgLevel &F, const MmgLevel &C, cons
 }
 
 // ------------------------------------------------------------------ smoother: KSPSolve_GMRES, left Jacobi, `its` iterations, no test
+// smoother PC: Jacobi, or ASM on the reference's element patches (Makefile:417)
+static int mmg_pc(xsb_ctx c, MmgLevel &L, int64_t n, const double *in, double *out)
+{ return L.asmpc ? asm_apply(c, L.asmpc, in, out) : vec_pmult(c, n, L.idiag, in, out); }
+
 static int mmg_smooth(xsb_ctx c, Mmg &G, MmgLevel &L, const double *b, double *x, int its, bool x_is_zero)
 {
   const int64_t n = L.ctx->lat.n; const Ranges rg = whole(n);
@@ -148,8 +167,8 @@ static int mmg_smooth(xsb_ctx c, Mmg &G, MmgLevel &L, const double *b, double *x
     const int m = its - done < G.restart ? its - done : G.restart;
     while ((int)L.V.size() < m + 1) { double *v = nullptr; XSB_CHK(dev_alloc(c, &v, (size_t)n)); L.V.push_back(v); }
     // r = B (b - A x)
-    if (x_is_zero && done == 0) XSB_CHK(vec_pmult(c, n, L.idiag, b, L.V[0]));
-    else { XSB_CHK(spmv_csr(c, L.ctx->A, x, L.t)); XSB_CHK(vec_aypx(c, n, -1.0, b, L.t)); XSB_CHK(vec_pmult(c, n, L.idiag, L.t, L.V[0])); }
+    if (x_is_zero && done == 0) XSB_CHK(mmg_pc(c, L, n, b, L.V[0]));
+    else { XSB_CHK(spmv_csr(c, L.ctx->A, x, L.t)); XSB_CHK(vec_aypx(c, n, -1.0, b, L.t)); XSB_CHK(mmg_pc(c, L, n, L.t, L.V[0])); }
     XSB_CHK(vec_mdot(c, rg, L.V[0], nullptr, 0, true, c->scal));
     double beta2; XSB_CHK(vec_fetch(c, c->scal, 1, &beta2));
     const double beta = sqrt(beta2);
@@ -160,7 +179,7 @@ static int mmg_smooth(xsb_ctx c, Mmg &G, MmgLevel &L, const double *b, double *x
     for (int j = 0; j < m; ++j) {
       double *w = L.V[j + 1];
       XSB_CHK(spmv_csr(c, L.ctx->A, L.V[j], L.t));
-      XSB_CHK(vec_pmult(c, n, L.idiag, L.t, w));                                   // w = B A v_j
+      XSB_CHK(mmg_pc(c, L, n, L.t, w));                                            // w = B A v_j
       XSB_CHK(vec_mdot(c, rg, w, L.V.data(), j + 1, false, c->scal));              // classical Gram-Schmidt, one pass
       XSB_CHK(vec_maxpy_dev(c, n, w, L.V.data(), j + 1, c->scal, -1.0));
       XSB_CHK(vec_mdot(c, rg, w, nullptr, 0, true, c->scal + j + 1));
@@ -219,6 +238,7 @@ void mmg_free(xsb_ctx c)
 {
   if (!c->mmg) return;
   Mmg *G = (Mmg *)c->mmg;
+  for (int l = 0; l < G->nlev; ++l) if (G->lev[l].asmpc) asm_free(G->lev[l].asmpc);
   for (int l = 0; l + 1 < G->nlev; ++l) { xsb_ctx ch = G->lev[l].ctx; if (ch) { dev_free_all(ch); delete ch; } }
   delete G; c->mmg = nullptr;
 }
@@ -232,8 +252,12 @@ int mmg_setup(xsb_ctx c)
   const int L = o.integer("nlevels", 1);
   if (L < 2) return xsb_fail(c, XSB_ERR_SUP, "-nlevels < 2 specified with -mg");                       // exSaddle.c:209
   if (L > XSB_MAX_LEVELS) return xsb_fail(c, XSB_ERR_SUP, "MG levels must be less than %d", XSB_MAX_LEVELS);   // :211
-  if (o.str("saddle_mg_levels_ksp_type", "chebyshev") != "gmres" || o.str("saddle_mg_levels_pc_type", "sor") != "jacobi")
-    return xsb_fail(c, XSB_ERR_SUP, "-mg smoothers: -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi (the reference's tests)");
+  const std::string spc = o.str("saddle_mg_levels_pc_type", "sor");
+  if (o.str("saddle_mg_levels_ksp_type", "chebyshev") != "gmres" || (spc != "jacobi" && spc != "asm"))
+    return xsb_fail(c, XSB_ERR_SUP, "-mg smoothers: -saddle_mg_levels_ksp_type gmres -saddle_mg_levels_pc_type jacobi|asm (the reference's tests)");
+  if (spc == "asm" && (!o.flag("saddle_mg_levels_pc_asm_dm_subdomains") || o.str("saddle_mg_levels_sub_pc_type", "ilu") != "lu" || o.str("saddle_mg_levels_sub_ksp_type", "preonly") != "preonly"))
+    return xsb_fail(c, XSB_ERR_SUP, "-saddle_mg_levels_pc_type asm is supported with the reference's element patches and exact sub-solves: -saddle_mg_levels_pc_asm_dm_subdomains -saddle_mg_levels_sub_pc_type lu");
+  o.has("saddle_mg_levels_sub_pc_factor_mat_solver_type");
   const int ratio = 1 << (L - 1);
   const int m[3] = {c->lat.mx, c->lat.my, nsd == 3 ? c->lat.mz : ratio};
   for (int d = 0; d < 3; ++d) {
@@ -270,6 +294,10 @@ int mmg_setup(xsb_ctx c)
     MmgLevel &lv = G->lev[k]; const int64_t n = lv.ctx->lat.n;
     XSB_CHK(dev_alloc(c, &lv.idiag, (size_t)n)); XSB_CHK(csr_diag_inv(c, lv.ctx->A, lv.idiag));
     XSB_CHK(dev_alloc(c, &lv.x, (size_t)n)); XSB_CHK(dev_alloc(c, &lv.b, (size_t)n)); XSB_CHK(dev_alloc(c, &lv.r, (size_t)n)); XSB_CHK(dev_alloc(c, &lv.t, (size_t)n));
+  }
+  if (spc == "asm") {   // one patch per rank of the communicator the reference would run on; every level's DMDA picks its own process grid
+    const int size = o.integer("xsb_ranks", 1), ov = o.integer("dmdafe_overlap", 0);
+    for (int k = 1; k < L; ++k) XSB_CHK(asm_setup(c, G->lev[k].ctx, size, ov, &G->lev[k].asmpc));
   }
   return dense_inverse_pivoted(c, G->lev[0].ctx->A, &G->lev[0].inv);
 }

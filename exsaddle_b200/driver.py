@@ -26,8 +26,10 @@ def diagnostics_text(nsd, d):
     return lines
 
 
-def run_exsaddle(exe, options, options_file_dir=None, outdir="."):
+def run_exsaddle(exe, options, options_file_dir=None, outdir=".", nranks=1):
     """exe in {exSaddle2d, exSaddle3d, exSaddle2d_lame, exSaddle3d_lame}; returns (stdout_text, ExSaddle, x).
+    nranks: the `mpiexec -n` of the reference's command line; it only matters where the reference's algorithm depends on the rank
+    count (one ASM element patch per rank) and is passed to the library as -xsb_ranks.
     -dump_solution / -dump_operator / -dump_scaled_mass_matrix write PETSc binary files into `outdir` under the
     reference's file names (exSaddle.c:488-501, 535-537)."""
     import os
@@ -43,6 +45,8 @@ def run_exsaddle(exe, options, options_file_dir=None, outdir="."):
         s.set_options_file(path)
     else:
         s.set_options(options)
+    if nranks > 1:
+        s.set_options("-xsb_ranks %d" % nranks)
     out = []
     out.append(s.banner().rstrip("\n"))
     s.assemble()

@@ -163,6 +163,17 @@ int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int 
 /* PCMG level lattice: DMCoarsen n -> (n-1)/2+1; returns 0 or XSB_ERR_ARG when not coarsenable */
 int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, int dims[3]);
 
+/* -------- ASM on the reference's element patches --------------------------------------- */
+/* Process grid PETSc's DMDACreate{2,3}d(PETSC_DECIDE) picks for M x N (x P) nodes on `size` ranks (the velocity DMDA of
+   femixedspace.c:1153-1158); XSB_ERR_ARG when `size` cannot be factored onto the lattice. */
+int xsb_dmda_grid(int nsd, int M, int N, int P, int size, int out[3]);
+/* Subdomain DMCreateDomainDecomposition_DMDAFEQ2Q1 (femixedspace.c:745-837) gives rank `rank` of `size` (x fastest in the process
+   grid) with -dmdafe_overlap `overlap`: out[0..2] first element and out[3..5] one past the last element of the closed patch,
+   out[6..8] / [9..11] the velocity-node range [lo,hi) the rank owns, out[12..14] / [15..17] the pressure-node range it owns.
+   XSB_ERR_ARG where the reference stops with "Cannot generate consistent macro element" (femixedspace.c:1097-1113).
+   The solver uses it with `-saddle_pc_type asm -saddle_pc_asm_dm_subdomains -set_ksp_dm -xsb_ranks <size>`. */
+int xsb_asm_subdomain(int nsd, int mx, int my, int mz, int size, int overlap, int rank, int out[18]);
+
 /* -------- multi-GPU: z-slab partition, one process per GPU ------------------------------------ */
 /* Element z-range [k0,k1) owned by `rank` of `nranks` (elements split like the reference's pressure rule,
    femixedspace.c:1231-1240: mz/nranks each, remainder to the low ranks). */

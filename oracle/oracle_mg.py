@@ -112,7 +112,7 @@ class Level:
 
 
 class MonolithicMG:
-    def __init__(self, opts, nsd=3, lame=False):
+    def __init__(self, opts, nsd=3, lame=False, nranks=1):
         self.o = O.parse_options(opts) if not isinstance(opts, dict) else dict(opts)
         o = self.o
         self.nsd, self.lame = nsd, lame
@@ -169,8 +169,18 @@ class MonolithicMG:
         self.fine = fine
         self.smooth_its = int(o.get("saddle_mg_levels_ksp_max_it", 2))   # PCMG default: 2 smoothing steps
         self.restart = int(o.get("saddle_mg_levels_ksp_gmres_restart", 30))
-        if o.get("saddle_mg_levels_ksp_type", "chebyshev") != "gmres" or o.get("saddle_mg_levels_pc_type", "sor") != "jacobi":
-            raise NotImplementedError("oracle -mg smoothers: gmres + jacobi (the reference's tests)")
+        spc = o.get("saddle_mg_levels_pc_type", "sor")
+        if o.get("saddle_mg_levels_ksp_type", "chebyshev") != "gmres" or spc not in ("jacobi", "asm"):
+            raise NotImplementedError("oracle -mg smoothers: gmres + jacobi | asm (the reference's tests)")
+        for k in range(L):
+            lv = self.levels[k]
+            lv.pc = (lambda d: (lambda v: d * v))(lv.idiag)
+        if spc == "asm":   # Makefile:418 (exSaddle3d_mg_asm_1): element-patch ASM with exact sub-solves as the smoother's PC, one patch per rank
+            from .oracle_asm import AsmPC
+            if "saddle_mg_levels_pc_asm_dm_subdomains" not in o or o.get("saddle_mg_levels_sub_pc_type", "ilu") != "lu":
+                raise NotImplementedError("oracle -mg ASM smoother: -saddle_mg_levels_pc_asm_dm_subdomains -saddle_mg_levels_sub_pc_type lu")
+            for k in range(1, L):
+                self.levels[k].pc = AsmPC(self.levels[k].A, nsd, mesh[k], nranks, int(o.get("dmdafe_overlap", 0)))
         self.n_smooth_mult = 0
 
     # -- KSPSolve_GMRES, left Jacobi, exactly `its` iterations from the current iterate (KSPConvergedSkip)
@@ -178,7 +188,7 @@ class MonolithicMG:
         done = 0
         while done < its:
             m = min(self.restart, its - done)
-            r = lv.idiag * (b - lv.A @ x); self.n_smooth_mult += 1
+            r = lv.pc(b - lv.A @ x); self.n_smooth_mult += 1
             beta = np.linalg.norm(r)
             if beta == 0.0:
                 return x
@@ -186,7 +196,7 @@ class MonolithicMG:
             V[0] = r / beta
             k = 0
             for j in range(m):
-                w = lv.idiag * (lv.A @ V[j]); self.n_smooth_mult += 1
+                w = lv.pc(lv.A @ V[j]); self.n_smooth_mult += 1
                 h = V[:j + 1] @ w                       # classical Gram-Schmidt, one pass
                 w = w - V[:j + 1].T @ h
                 hn = np.linalg.norm(w)

@@ -209,10 +209,10 @@ def test_abf_solve_history_matches_oracle(abf_pair):
 
 
 # ------------------------------------------------------------------ the reference's golden outputs, end to end
-def _run(kat, name, extra=""):
+def _run(kat, name, extra="", nranks=1):
     c = kat[name]
     opts = c["options"].replace("-options_file abf.opts", ABF) + " " + extra
-    text, s, x = X.run_exsaddle(c["exe"], opts)
+    text, s, x = X.run_exsaddle(c["exe"], opts, nranks=nranks)
     return c, text, s, x
 
 
@@ -444,6 +444,45 @@ def test_monolithic_mg_option_errors_like_reference():
 
 
 # ------------------------------------------------------------------ BASELINE sizes against committed oracle fixtures
+@pytest.mark.parametrize("name", ["exSaddle2d_asm_1", "exSaddle3d_asm_1", "exSaddle3d_mg_asm_1"])
+def test_golden_asm_element_patches_output_is_identical(kat, name):
+    """ASM on the reference's element patches, one per rank of the golden's communicator (-xsb_ranks 9 / 8 / 4),
+    dense pivoted inverses + one-launch apply on the device -- as the top-level PC (Makefile:298, 411) and as the PC of the -mg
+    GMRES smoother (:418).  The program output matches testref/*.ref (one last-digit difference allowed)."""
+    c, text, s, x = _run(kat, name, nranks=kat[name]["nranks"])
+    ref = list(c["banner"]) + ["  Residual norms for saddle_ solve."] + ["%3d KSP Residual norm %s" % (i, t) for i, t in enumerate(c["residuals_text"])]
+    got = [l.rstrip() for l in text.rstrip("\n").split("\n")]
+    # the sub-solves are exact but not UMFPACK's: at most one residual may differ, by one unit of its sixth digit
+    assert len(got) == len(ref) and sum(a != b for a, b in zip(got, ref)) <= 1
+    assert np.allclose(s.history(), c["residuals"], rtol=6e-6, atol=0)   # six printed digits
+
+
+@pytest.mark.parametrize("nsd,size,opts", [(2, 6, "-model 6 -mx 8 -my 5 -eta1 100 -dmdafe_overlap 1"), (3, 5, "-model 1 -mx 4 -my 3 -mz 10 -eta1 10 -dmdafe_overlap 1"),
+                                           (3, 1, "-model 6 -mx 3 -eta1 1e3")])
+def test_asm_pc_apply_and_solve_match_oracle(nsd, size, opts):
+    """PC apply <= 1e-9 (exact dense sub-solves of indefinite patches against SuperLU), iteration count and history against the oracle;
+    one rank = one patch = a direct solve (1 iteration)."""
+    from oracle import oracle_asm as OA
+    full = "-saddle_pc_type asm -saddle_pc_asm_dm_subdomains -set_ksp_dm -saddle_sub_ksp_type preonly -saddle_sub_pc_type lu -saddle_ksp_rtol 1e-8 " + opts
+    xo, its, reason, hist, p = OA.solve(full, nsd, size)
+    g = X.ExSaddle(full + " -xsb_ranks %d" % size, nsd=nsd).assemble().ksp_setup()
+    A = p.A().scipy().tocsr()
+    o = O.parse_options(full); mx = int(o.get("mx", 4)); my = int(o.get("my", mx)); mz = int(o.get("mz", mx)) if nsd == 3 else 1
+    pc = OA.AsmPC(A, nsd, (mx, my, mz), size, int(o.get("dmdafe_overlap", 0)))
+    r = np.cos(0.7 * np.arange(p.n)) + 0.3
+    zg = g.pc_apply(r); zo = pc(r)
+    assert np.linalg.norm(zg - zo) <= 1e-9 * np.linalg.norm(zo)
+    x = g.solve()
+    gi, gr = g.iterations()
+    assert gr == reason and abs(gi - its) <= 1     # 100+ iterations with restarts: rounding may move the last one across the tolerance
+    h = g.history(); k = min(len(h), len(hist), 31)
+    assert np.max(np.abs(h[:k] - np.array(hist[:k]))) <= 1e-8 * hist[0]    # first restart cycle
+    if size == 1:
+        assert its == 1
+    assert np.linalg.norm(x - xo) <= 1e-6 * np.linalg.norm(xo)
+    g.close()
+
+
 @pytest.mark.parametrize("mx,levels", [(32, 5), (64, 6)])
 def test_baseline_size_history_matches_oracle_fixture(mx, levels):
     """bench.py's workloads (configs[1] 32^3, configs[2] 64^3): the GPU residual history against the CPU oracle's, generated

@@ -399,6 +399,55 @@ def test_monolithic_mg_fs_coarse_golden(kat):
     assert M.fine.banner.rstrip("\n").split("\n") == c["banner"]
 
 
+# ---- ASM on the reference's element patches (oracle/oracle_asm.py) ----
+@pytest.mark.parametrize("name", ["exSaddle2d_asm_1", "exSaddle3d_asm_1"])
+def test_asm_element_patch_goldens(kat, name):
+    """`-saddle_pc_type asm -saddle_pc_asm_dm_subdomains -set_ksp_dm` on 9 / 8 ranks (Makefile:298, 411): one closed element patch per
+    rank (+ -dmdafe_overlap), exact sub-solves, sub-solutions kept on the rank's owned dofs (PC_ASM_RESTRICT): every printed digit
+    of every residual of testref/exSaddle{2d,3d}_asm_1.ref (one last-digit rounding difference allowed)."""
+    from oracle import oracle_asm as OA
+    c = kat[name]
+    x, its, reason, hist, p = OA.solve(c["options"], c["nsd"], c["nranks"])
+    assert reason == 2 and its == len(c["residuals"]) - 1
+    # every printed digit, up to one unit of the sixth digit (SuperLU here, UMFPACK there: 4.97997e-05 against 4.97998e-05 at iteration 23 in 3-D)
+    assert np.allclose(hist, c["residuals"], rtol=6e-6, atol=0)   # six printed digits
+    assert sum(a != b for a, b in zip([_short(v) for v in hist], c["residuals_text"])) <= 1
+    assert p.banner.rstrip("\n").split("\n") == c["banner"]
+
+
+def test_asm_smoother_inside_monolithic_mg_golden(kat):
+    """`-mg -nlevels 2 -saddle_mg_levels_pc_type asm -saddle_mg_levels_pc_asm_dm_subdomains -dmdafe_overlap 1` on 4 ranks, 6 x 4 x 4
+    elements (Makefile:418): the same patches as the PC of the GMRES smoother; testref/exSaddle3d_mg_asm_1.ref digit for digit."""
+    from oracle.oracle_mg import MonolithicMG
+    c = kat["exSaddle3d_mg_asm_1"]
+    M = MonolithicMG(c["options"], nsd=3, nranks=c["nranks"])
+    x, its, reason, hist = M.solve()
+    assert reason == 2 and [_short(v) for v in hist] == c["residuals_text"]
+
+
+def test_asm_subdomains_host_logic_matches_oracle_and_tiles_the_mesh():
+    """xsb_dmda_grid / xsb_asm_subdomain (host integer logic of the product, no GPU) against the oracle's restatement of PETSc's
+    DMDA partition + the reference's element fitting: process grids, patches, owned ranges; owned ranges tile both lattices."""
+    import exsaddle_b200 as X
+    from oracle import oracle_asm as OA
+    for nsd, mesh, size, ov in [(2, (12, 12, 1), 9, 1), (3, (6, 6, 6), 8, 0), (3, (6, 4, 4), 4, 1), (2, (8, 5, 1), 6, 0), (3, (8, 8, 8), 12, 2),
+                                (3, (4, 6, 10), 5, 1), (2, (16, 4, 1), 4, 1), (3, (64, 64, 64), 64, 1), (2, (7, 9, 1), 1, 3)]:
+        grid, sds = OA.subdomains(nsd, mesh, size, ov)
+        N = [2 * m + 1 for m in mesh]
+        assert X.dmda_grid(nsd, N[0], N[1], N[2] if nsd == 3 else 1, size)[:nsd] == tuple(grid[:nsd])
+        cover_u = np.zeros(N[:nsd][::-1], int); cover_p = np.zeros([m + 1 for m in mesh[:nsd]][::-1], int)
+        for r, sd in enumerate(sds):
+            got = X.asm_subdomain(nsd, mesh[0], mesh[1], mesh[2], size, ov, r)
+            assert got == sd, (nsd, mesh, size, r)
+            su = tuple(slice(a, b) for a, b in got["own_u"][::-1]); spp = tuple(slice(a, b) for a, b in got["own_p"][::-1])
+            cover_u[su] += 1; cover_p[spp] += 1
+            for d in range(nsd):   # owned nodes lie inside the rank's patch
+                assert 2 * got["lo"][d] <= got["own_u"][d][0] and got["own_u"][d][1] <= 2 * got["hi"][d] + 1
+        assert np.all(cover_u == 1) and np.all(cover_p == 1)
+    with pytest.raises(X.XsbError):     # 3 ranks on 5 nodes per direction: no rank can hold a whole element column (femixedspace.c:1097)
+        X.asm_subdomain(2, 2, 2, 1, 9, 0, 0)
+
+
 # ---- the reference's plain -fs tree with PETSc's default sub-solvers (oracle only; oracle/oracle_fs.py) ----
 @pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1"])
 def test_plain_fs_tree_history_and_diagnostics_match_golden(kat, name):
