@@ -309,6 +309,10 @@ int dense_invert_pivoted(xsb_ctx c, int n, double *M, double *Inv);
 int fsd_setup(xsb_ctx c);
 int fsd_apply(xsb_ctx c, const double *r, double *z);
 void fsd_free(xsb_ctx c);
+int fsc_setup(xsb_ctx alloc, xsb_ctx coarse_problem, void **out);   // -fs_coarse: fieldsplit-preconditioned FGMRES on the coarse -mg level
+int fsc_solve(xsb_ctx c, void *fsc, const double *b, double *x);
+int fsc_last_its(void *fsc);
+void fsc_free(void *fsc);
 // ---- xsb_ilu.cu
 int ilu_setup(xsb_ctx c);
 int ilu_apply(xsb_ctx c, const double *b, double *x);

@@ -196,7 +196,115 @@ int gmres_left(xsb_ctx c, int64_t n, const Op &A, const Op &M, const double *b, 
   if (its_out) *its_out = its;
   return 0;
 }
+
+// KSPSolve_FGMRES from a zero initial guess: right (flexible) PC, unpreconditioned norm, classical Gram-Schmidt, restart m (App. B.5)
+int fgmres_right(xsb_ctx c, int64_t n, const Op &A, const Op &M, const double *b, double *x, double rtol, int max_it, int m,
+                 std::vector<double *> &V, std::vector<double *> &Z, double *t1, double *scal, int *its_out)
+{
+  const Ranges rg = whole(n);
+  std::vector<double> hh((size_t)(m + 1) * m), cs(m + 1), sn(m + 1), rs(m + 1), y(m + 1), hcol(m + 2);
+  auto need = [&](std::vector<double *> &W, int k) -> int { while ((int)W.size() <= k) { double *p = nullptr; c->phase = 1; int rc = dev_alloc(c, &p, (size_t)n); c->phase = 0; if (rc) return rc; W.push_back(p); } return 0; };
+  int its = 0, reason = 0; double rnorm0 = 0.0, ttol = 0.0; bool first = true;
+  XSB_CHK(vec_set(c, n, 0.0, x)); XSB_CHK(need(V, 0));
+  while (!reason) {
+    if (first) XSB_CHK(vec_copy(c, n, b, V[0]));
+    else { XSB_CHK(A(x, t1)); XSB_CHK(vec_aypx(c, n, -1.0, b, t1)); XSB_CHK(vec_copy(c, n, t1, V[0])); }
+    first = false;
+    XSB_CHK(vec_mdot(c, rg, V[0], nullptr, 0, true, scal, true));
+    XSB_CHK(vec_fetch(c, scal, 1, hcol.data()));
+    double res = sqrt(hcol[0]);
+    if (its == 0) { rnorm0 = res; ttol = fmax(rtol * rnorm0, 1e-50); }
+    if (res == 0.0 || res <= ttol) { reason = 2; break; }
+    if (its >= max_it) { reason = -3; break; }
+    XSB_CHK(vec_scale(c, n, 1.0 / res, V[0]));
+    rs[0] = res;
+    int it = 0;
+    while (!reason && it < m && its < max_it) {
+      XSB_CHK(need(V, it + 1)); XSB_CHK(need(Z, it));
+      double *w = V[it + 1];
+      XSB_CHK(M(V[it], Z[it])); XSB_CHK(A(Z[it], w));
+      XSB_CHK(vec_mdot(c, rg, w, V.data(), it + 1, false, scal, true));
+      XSB_CHK(vec_maxpy_dev(c, n, w, V.data(), it + 1, scal, -1.0));
+      XSB_CHK(vec_mdot(c, rg, w, nullptr, 0, true, scal + it + 1, true));
+      XSB_CHK(vec_scale_by_inv_sqrt(c, n, w, scal + it + 1));
+      XSB_CHK(vec_fetch(c, scal, it + 2, hcol.data()));
+      hcol[it + 1] = sqrt(hcol[it + 1]);
+      for (int j = 0; j < it; ++j) { double t = hcol[j]; hcol[j] = cs[j] * t + sn[j] * hcol[j + 1]; hcol[j + 1] = -sn[j] * t + cs[j] * hcol[j + 1]; }
+      const double tt = sqrt(hcol[it] * hcol[it] + hcol[it + 1] * hcol[it + 1]);
+      if (tt == 0.0) { reason = -5; break; }
+      cs[it] = hcol[it] / tt; sn[it] = hcol[it + 1] / tt;
+      rs[it + 1] = -sn[it] * rs[it]; rs[it] = cs[it] * rs[it];
+      hcol[it] = cs[it] * hcol[it] + sn[it] * hcol[it + 1]; hcol[it + 1] = 0.0;
+      res = fabs(rs[it + 1]);
+      for (int j = 0; j <= it; ++j) hh[(size_t)it * (m + 1) + j] = hcol[j];
+      it++; its++;
+      if (res <= ttol) reason = 2; else if (res >= 1e4 * rnorm0) reason = -4; else if (its >= max_it) reason = -3;
+    }
+    if (it > 0) {
+      for (int k = it - 1; k >= 0; --k) { double t = rs[k]; for (int j = k + 1; j < it; ++j) t -= hh[(size_t)j * (m + 1) + k] * y[j]; y[k] = t / hh[(size_t)k * (m + 1) + k]; }
+      CUDA_OK(cudaMemcpyAsync(scal + 32, y.data(), sizeof(double) * it, cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+      XSB_CHK(vec_maxpy_dev(c, n, x, Z.data(), it, scal + 32, 1.0));
+    }
+  }
+  if (its_out) *its_out = its;
+  return 0;
+}
+
+// -fs_coarse (exSaddle.c:362-400): the coarse level of the monolithic -mg hierarchy solved by FGMRES preconditioned with
+// PCFIELDSPLIT Schur / UPPER / user Mpscaled_coarse, both splits GMRES + Jacobi, the Schur complement applied with a nested
+// velocity solve (golden exSaddle3d_mg_fs_coarse_1, Makefile:390; solver tree as its -saddle_ksp_view prints it).
+struct FsCoarse {
+  xsb_ctx P = nullptr; double *id00 = nullptr, *idmp = nullptr;
+  std::vector<double *> Vu, Vp, Vo, Zo; double *u_t1 = nullptr, *u_t2 = nullptr, *u_rhs = nullptr, *u_sol = nullptr, *p_t1 = nullptr, *p_t2 = nullptr, *p_tmp = nullptr, *o_t1 = nullptr, *pc_z = nullptr;
+  double rtol = 1e-5, u_rtol = 1e-5, p_rtol = 1e-5; int max_it = 10000; std::vector<int> its;
+};
 }   // namespace
+
+void fsc_free(void *h) { delete (FsCoarse *)h; }
+int fsc_setup(xsb_ctx c, xsb_ctx P, void **out)
+{
+  Options &o = c->opt; const Lattice &L = P->lat;
+  const char *need[][2] = {{"saddle_mg_coarse_ksp_type", "fgmres"}, {"saddle_mg_coarse_fieldsplit_u_pc_type", "jacobi"}, {"saddle_mg_coarse_fieldsplit_p_pc_type", "jacobi"}, {"saddle_mg_coarse_ksp_convergence_test", "default"}};
+  for (auto &kv : need) if (o.str(kv[0], "") != kv[1]) return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse is supported with the reference's coarse tree: -%s %s (Makefile:390)", kv[0], kv[1]);
+  if (o.str("saddle_mg_coarse_fieldsplit_u_ksp_type", "gmres") != "gmres" || o.str("saddle_mg_coarse_fieldsplit_p_ksp_type", "gmres") != "gmres") return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse: the coarse splits use gmres");
+  FsCoarse *F = new FsCoarse(); *out = F; F->P = P;
+  F->rtol = o.real("saddle_mg_coarse_ksp_rtol", 1e-5); F->max_it = o.integer("saddle_mg_coarse_ksp_max_it", 10000);
+  F->u_rtol = o.real("saddle_mg_coarse_fieldsplit_u_ksp_rtol", 1e-5); F->p_rtol = o.real("saddle_mg_coarse_fieldsplit_p_ksp_rtol", 1e-5);
+  XSB_CHK(dev_alloc(c, &F->id00, (size_t)L.nu)); XSB_CHK(baij_diag_inv(c, P->A00, F->id00));
+  XSB_CHK(dev_alloc(c, &F->idmp, (size_t)L.np)); XSB_CHK(csr_diag_inv(c, P->Mp, F->idmp));
+  for (double **v : {&F->u_t1, &F->u_t2, &F->u_rhs, &F->u_sol}) XSB_CHK(dev_alloc(c, v, (size_t)L.nu));
+  for (double **v : {&F->p_t1, &F->p_t2, &F->p_tmp}) XSB_CHK(dev_alloc(c, v, (size_t)L.np));
+  XSB_CHK(dev_alloc(c, &F->o_t1, (size_t)L.n)); XSB_CHK(dev_alloc(c, &F->pc_z, (size_t)L.n));
+  return 0;
+}
+int fsc_solve(xsb_ctx c, void *h, const double *b, double *x)
+{
+  FsCoarse *F = (FsCoarse *)h; xsb_ctx P = F->P; const Lattice &L = P->lat; const int64_t nu = L.nu, np = L.np;
+  Epilogue plain;
+  Op A00 = [&](const double *v, double *y) { return spmv_baij(c, P->A00, v, y, plain); };
+  Op Mu = [&](const double *v, double *y) { return vec_pmult(c, nu, F->id00, v, y); };
+  Op Mp = [&](const double *v, double *y) { return vec_pmult(c, np, F->idmp, v, y); };
+  auto ksp_u = [&](const double *rhs, double *sol) { return gmres_left(c, nu, A00, Mu, rhs, sol, F->u_rtol, 10000, 30, F->Vu, F->u_t1, F->u_t2, c->scal, nullptr); };
+  Op S = [&](const double *v, double *y) {
+    XSB_CHK(spmv_csr(c, P->A01, v, F->u_rhs));
+    XSB_CHK(ksp_u(F->u_rhs, F->u_sol));
+    XSB_CHK(spmv_csr(c, P->A10, F->u_sol, F->p_tmp));
+    XSB_CHK(spmv_csr(c, P->A11, v, y));
+    return vec_axpy(c, np, -1.0, F->p_tmp, y); };
+  Op PC = [&](const double *r, double *z) {
+    double *yu = z, *yp = z + nu;
+    XSB_CHK(gmres_left(c, np, S, Mp, r + nu, yp, F->p_rtol, 10000, 30, F->Vp, F->p_t1, F->p_t2, c->scal + 96, nullptr));
+    XSB_CHK(spmv_csr(c, P->A01, yp, F->u_rhs));
+    XSB_CHK(vec_aypx(c, nu, -1.0, r, F->u_rhs));
+    return ksp_u(F->u_rhs, yu); };
+  Op A = [&](const double *v, double *y) { return spmv_csr(c, P->A, v, y); };
+  int its = 0;
+  XSB_CHK(fgmres_right(c, L.n, A, PC, b, x, F->rtol, F->max_it, 30, F->Vo, F->Zo, F->o_t1, c->scal + 192, &its));
+  F->its.push_back(its);
+  return 0;
+}
+int fsc_last_its(void *h) { FsCoarse *F = (FsCoarse *)h; return F->its.empty() ? 0 : F->its.back(); }
 
 void fsd_free(xsb_ctx c) { if (c->fsd) { delete (Fsd *)c->fsd; c->fsd = nullptr; } }
 

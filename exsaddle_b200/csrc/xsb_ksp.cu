@@ -149,12 +149,13 @@ static int read_solver_options(xsb_ctx c)
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_ksp_type %s not supported (gmres|fgmres)", ksp.c_str());
   const bool fs = o.flag("fs"), mg = o.flag("mg");
   if (fs && mg) return xsb_fail(c, XSB_ERR_SUP, "both -fs and -mg supplied");              // exSaddle.c:205
+  if (o.flag("fs_coarse") && !mg) return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse supplied without -mg");   // exSaddle.c:210
   if (o.integer("nlevels", 1) > 1 && fs) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified with -fs");      // exSaddle.c:207
   if (o.integer("nlevels", 1) > 1 && !mg) return xsb_fail(c, XSB_ERR_SUP, "-nlevels > 1 specified without -mg"); // exSaddle.c:208
   if (o.flag("set_ksp_dm") && (mg || fs)) return xsb_fail(c, XSB_ERR_SUP, "-set_ksp_dm not intended for use with -mg or -fs");   // exSaddle.c:212
   if (mg) {
     s.pc_type = 3;   // monolithic PCMG on the saddle operator (xsb_mmg.cu)
-    if (o.flag("fs_coarse")) return xsb_fail(c, XSB_ERR_SUP, "-fs_coarse (fieldsplit coarse solver) is not implemented");
+    o.has("fs_coarse");   // fieldsplit coarse solver: validated in mmg_setup / fsc_setup
   } else if (fs && o.str("saddle_fieldsplit_u_pc_type", "") != "mg") {
     s.pc_type = 4;   // plain -fs: PETSc's default sub-solvers (GMRES + ILU(0) on A00, nested Schur solves); validated in fsd_setup (xsb_fs.cu)
     o.has("saddle_fieldsplit_u_ksp_type"); o.has("saddle_fieldsplit_p_ksp_type"); o.has("saddle_fieldsplit_u_ksp_max_it"); o.has("saddle_fieldsplit_p_pc_type");

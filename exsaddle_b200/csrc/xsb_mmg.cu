@@ -22,6 +22,7 @@ struct MmgLevel {
   double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
   std::vector<double *> V;    // GMRES basis of the smoother
   double *inv = nullptr;      // coarsest: dense inverse
+  void *fsc = nullptr;        // coarsest with -fs_coarse: fieldsplit-preconditioned FGMRES instead of the dense inverse (xsb_fs.cu)
   void *asmpc = nullptr;      // -saddle_mg_levels_pc_type asm: element-patch ASM instead of Jacobi (xsb_asm.cu)
 };
 struct Mmg { int nlev = 0, smooth_its = 2, restart = 30; std::vector<MmgLevel> lev; };
@@ -212,6 +213,7 @@ static int mmg_cycle(xsb_ctx c, Mmg &G, int l)
 {
   MmgLevel &L = G.lev[l];
   const int64_t n = L.ctx->lat.n;
+  if (l == 0 && L.fsc) return fsc_solve(c, L.fsc, L.b, L.x);
   if (l == 0) { k_gemv_rows<<<nblk((int64_t)n * 32), 256, 0, c->stream>>>((int)n, L.inv, L.b, L.x); KERNEL_OK(); return 0; }
   MmgLevel &C = G.lev[l - 1];
   XSB_CHK(vec_set(c, n, 0.0, L.x));
@@ -238,7 +240,7 @@ void mmg_free(xsb_ctx c)
 {
   if (!c->mmg) return;
   Mmg *G = (Mmg *)c->mmg;
-  for (int l = 0; l < G->nlev; ++l) if (G->lev[l].asmpc) asm_free(G->lev[l].asmpc);
+  for (int l = 0; l < G->nlev; ++l) { if (G->lev[l].asmpc) asm_free(G->lev[l].asmpc); if (G->lev[l].fsc) fsc_free(G->lev[l].fsc); }
   for (int l = 0; l + 1 < G->nlev; ++l) { xsb_ctx ch = G->lev[l].ctx; if (ch) { dev_free_all(ch); delete ch; } }
   delete G; c->mmg = nullptr;
 }
@@ -299,5 +301,6 @@ int mmg_setup(xsb_ctx c)
     const int size = o.integer("xsb_ranks", 1), ov = o.integer("dmdafe_overlap", 0);
     for (int k = 1; k < L; ++k) XSB_CHK(asm_setup(c, G->lev[k].ctx, size, ov, &G->lev[k].asmpc));
   }
+  if (o.flag("fs_coarse")) return fsc_setup(c, G->lev[0].ctx, &G->lev[0].fsc);   // exSaddle.c:362-400
   return dense_inverse_pivoted(c, G->lev[0].ctx->A, &G->lev[0].inv);
 }

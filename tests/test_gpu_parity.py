@@ -443,6 +443,27 @@ def test_monolithic_mg_option_errors_like_reference():
         g.close()
 
 
+def test_golden_monolithic_mg_fs_coarse(kat):
+    """-mg -fs_coarse (exSaddle.c:362-400, Makefile:390): the coarse saddle level solved by FGMRES preconditioned with fieldsplit
+    Schur / UPPER / user Mpscaled_coarse (GMRES + Jacobi splits, nested velocity solve inside the Schur complement), on the device.
+    testref/exSaddle3d_mg_fs_coarse_1.ref: 13 iterations, CONVERGED_RTOL, the first six residuals to every printed digit, all to
+    3e-5 (the nested inexact solves at rtol 1e-5 amplify summation-order differences: the oracle meets the same bar); and the
+    oracle's history to 1e-4 entry-wise."""
+    from oracle.oracle_mg import MonolithicMG
+    c = kat["exSaddle3d_mg_fs_coarse_1"]
+    opts = c["options"].replace("-saddle_ksp_view", "")
+    g = X.ExSaddle(opts, nsd=3).assemble().ksp_setup()
+    g.solve()
+    its, reason = g.iterations(); h = g.history()
+    assert (its, reason) == (c["iterations"], 2) and len(h) == len(c["residuals"])
+    assert [X.monitor_short(v) for v in h[:6]] == c["residuals_text"][:6]
+    assert np.allclose(h, c["residuals"], rtol=3e-5, atol=0)
+    M = MonolithicMG(c["options"], nsd=3)
+    xo, ito, ro, ho = M.solve()
+    assert ito == its and np.allclose(h, ho, rtol=1e-4, atol=0)
+    g.close()
+
+
 # ------------------------------------------------------------------ BASELINE sizes against committed oracle fixtures
 @pytest.mark.parametrize("name", ["exSaddle2d_asm_1", "exSaddle3d_asm_1", "exSaddle3d_mg_asm_1"])
 def test_golden_asm_element_patches_output_is_identical(kat, name):

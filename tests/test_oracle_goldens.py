@@ -386,8 +386,8 @@ def test_monolithic_mg_fs_coarse_golden(kat):
     FGMRES preconditioned by PCFIELDSPLIT Schur / UPPER / user Mpscaled_coarse with GMRES + Jacobi on both splits and the nested
     A00 solve inside every Schur-complement product (App. B.2; solver tree as printed by -saddle_ksp_view in the golden).
     13 iterations and CONVERGED_RTOL as in testref/exSaddle3d_mg_fs_coarse_1.ref; residuals to 3e-5 (the nested inexact solves
-    at rtol 1e-5 amplify summation-order differences; the first six agree to all printed digits).  Oracle only: the product
-    rejects -fs_coarse with XSB_ERR_SUP."""
+    at rtol 1e-5 amplify summation-order differences; the first six agree to all printed digits).  The product runs the same tree on
+    the device: tests/test_gpu_parity.py::test_golden_monolithic_mg_fs_coarse."""
     from oracle.oracle_mg import MonolithicMG
     c = kat["exSaddle3d_mg_fs_coarse_1"]
     M = MonolithicMG(c["options"], nsd=3)
