@@ -202,9 +202,7 @@ int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilog
   const int tpb = 256; int64_t blocks = ((int64_t)nnodes * 32 + tpb - 1) / tpb;
   const int64_t cap = 148LL * 8 * 16;
   if (blocks > cap) blocks = cap;
-  // 27-point levels (every Galerkin level): a row is 27 blocks = 9 warp iterations -- one batch of 9 loads in flight instead of 8 + 1
-  if (A.bs == 3 && !A.pat.q2 && A.pat.nx > 0) spmv_baij_kernel<3, 9><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
-  else if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
+  if (A.bs == 3) spmv_baij_kernel<3, 8><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
   else if (A.bs == 2) spmv_baij_kernel<2, 4><<<(unsigned)blocks, tpb, 0, c->stream>>>(node0, nnodes, A.ia, A.ja, A.a, x, y, ep);
   else return xsb_fail(c, XSB_ERR_SUP, "BAIJ block size %d", A.bs);
   KERNEL_OK();
