@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libexsaddle_b200.so")
 
-MAT_A, MAT_A00, MAT_A01, MAT_A10, MAT_A11, MAT_MP, MAT_A00_MF, MAT_MG_LEVEL0 = 0, 1, 2, 3, 4, 5, 6, 16
+MAT_A, MAT_A00, MAT_A01, MAT_A10, MAT_A11, MAT_MP, MAT_A00_MF, MAT_A01_MF, MAT_A10_MF, MAT_MG_LEVEL0 = 0, 1, 2, 3, 4, 5, 6, 7, 8, 16
 ERR_NO_DEVICE = -6
 
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libexsaddle_b200.so")
-SOURCES = ["xsb_api.cu", "xsb_fe.cu", "xsb_spmv.cu", "xsb_vec.cu", "xsb_mg.cu", "xsb_ilu.cu", "xsb_ksp.cu", "xsb_mf.cu", "xsb_mf1p.cu", "xsb_mfull.cu", "xsb_mmg.cu", "xsb_fs.cu", "xsb_asm.cu", "xsb_io.cu", "xsb_comm.cu"]
+SOURCES = ["xsb_api.cu", "xsb_fe.cu", "xsb_spmv.cu", "xsb_vec.cu", "xsb_mg.cu", "xsb_ilu.cu", "xsb_ksp.cu", "xsb_mf.cu", "xsb_mf1p.cu", "xsb_mfull.cu", "xsb_mmg.cu", "xsb_fs.cu", "xsb_asm.cu", "xsb_grad.cu", "xsb_io.cu", "xsb_comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", "/usr/bin/g++",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -156,6 +156,7 @@ struct SolverOpts {
   int mf_kernel = 4;     // -xsb_mf_kernel: 4 = one-pass TMA-staged kernel (xsb_mf1p.cu), 3 = 8-colour kernel (xsb_mf.cu)
   int mf_reverse = 1;    // -xsb_mf_reverse: successive colour launches sweep the mesh in alternating directions (L2 reuse)
   int mf_chunk = 0;      // -xsb_mf_chunk: element layers per z-chunk of the matrix-free apply (0 = sized for L2)
+  int mf_grad = 0;       // -xsb_mf_grad: A01 / A10 products by the closed-form gradient / divergence stencils (xsb_grad.cu); default on in operator-free mode
   int matrix_free = 0;   // -xsb_matrix_free: fine-level A00 products by the sum-factorised element kernel (xsb_mf.cu)
 };
 
@@ -300,6 +301,9 @@ int mg_prolong_add_scalar(xsb_ctx c, int fnx, int fny, int fnz, int cnx, int cny
 int mmg_setup(xsb_ctx c);
 int mmg_apply(xsb_ctx c, const double *r, double *z);
 void mmg_free(xsb_ctx c);
+// ---- xsb_grad.cu (gradient / divergence blocks matrix-free)
+int grad_apply(xsb_ctx c, const double *xp, double *y, int64_t dof0, int64_t ndofs, const double *yadd = nullptr);   // y_u rows = A01 xp (+ yadd)
+int div_apply(xsb_ctx c, const double *xu, double *y, int64_t p0, int64_t np, const double *yadd = nullptr);         // y_p rows = A10 xu (+ yadd)
 // ---- xsb_asm.cu (additive Schwarz on the reference's element patches)
 int asm_setup(xsb_ctx alloc, xsb_ctx problem, int size, int overlap, void **out);
 int asm_apply(xsb_ctx c, void *asmpc, const double *r, double *z);

@@ -203,8 +203,8 @@ static int pick_csr(xsb_ctx c, int which, const Csr **S, const Baij **B)
   switch (which) {
   case XSB_MAT_A: *S = &c->A; return 0;
   case XSB_MAT_A00: case XSB_MAT_A00_MF: *B = &c->A00; return 0;
-  case XSB_MAT_A01: *S = &c->A01; return 0;
-  case XSB_MAT_A10: *S = &c->A10; return 0;
+  case XSB_MAT_A01: case XSB_MAT_A01_MF: *S = &c->A01; return 0;
+  case XSB_MAT_A10: case XSB_MAT_A10_MF: *S = &c->A10; return 0;
   case XSB_MAT_A11: *S = &c->A11; return 0;
   case XSB_MAT_MP: *S = &c->Mp; return 0;
   default:
@@ -249,6 +249,8 @@ int xsb_mat_mult_dev(xsb_ctx c, int which, const double *x, double *y)
     if (which == XSB_MAT_A00) which = XSB_MAT_A00_MF;
   }
   const Csr *S; const Baij *B; XSB_CHK(pick_csr(c, which, &S, &B));
+  if (which == XSB_MAT_A01_MF) return grad_apply(c, x, y, 0, c->lat.nu);
+  if (which == XSB_MAT_A10_MF) return div_apply(c, x, y, 0, c->lat.np);
   if (S) return which == XSB_MAT_A ? op_full_mult(c, x, y) : spmv_csr(c, *S, x, y);
   Epilogue ep;
   if (which == XSB_MAT_A00_MF) { XSB_CHK(mf_setup(c)); return mf_a00_apply(c, x, y, ep); }

@@ -63,6 +63,11 @@ int op_full_mult(xsb_ctx c, const double *x, double *y)
     XSB_CHK(mf_setup(c));   // returns at once when the element-kernel state is current (the product may precede xsb_ksp_setup)
     XSB_CHK(comm_halo_full(c, const_cast<double *>(x)));
     XSB_CHK(mf_a00_apply(c, x, y, ep));
+    if (c->so.mf_grad || !c->ksp_ready) {   // gradient / divergence by their closed-form stencils: no matrix read (before the first set-up: the default of this mode)
+      XSB_CHK(grad_apply(c, x + L.nu, y, c->own_u.off0, c->own_u.len0, y));
+      XSB_CHK(spmv_csr(c, c->A11, x + L.nu, y + L.nu, c->own_p.off0, c->own_p.len0));
+      return div_apply(c, x, y + L.nu, c->own_p.off0, c->own_p.len0, y + L.nu);
+    }
     XSB_CHK(spmv_csr(c, c->A01, x + L.nu, y, c->own_u.off0, c->own_u.len0, y));
     XSB_CHK(spmv_csr(c, c->A11, x + L.nu, y + L.nu, c->own_p.off0, c->own_p.len0));
     return spmv_csr(c, c->A10, x, y + L.nu, c->own_p.off0, c->own_p.len0, y + L.nu);
@@ -130,7 +135,8 @@ int pc_apply(xsb_ctx c, const double *r, double *z, int *inner, int *inner_reaso
   if (c->so.p_pc == 0) XSB_CHK(ilu_apply(c, r + L.nu + c->own_p.off0, yp + c->own_p.off0)); else XSB_CHK(vec_pmult(c, L.np, c->mp_idiag, r + L.nu, yp));
   XSB_CHK(prof_mark(c, PROF_CSR));
   XSB_CHK(comm_halo_p(c, yp));
-  XSB_CHK(spmv_csr(c, c->A01, yp, c->fs_tu, c->own_u.off0, c->own_u.len0));
+  if (c->so.mf_grad) XSB_CHK(grad_apply(c, yp, c->fs_tu, c->own_u.off0, c->own_u.len0));
+  else XSB_CHK(spmv_csr(c, c->A01, yp, c->fs_tu, c->own_u.off0, c->own_u.len0));
   XSB_CHK(prof_mark(c, PROF_OTHER));
   XSB_CHK(vec_aypx(c, L.nu, -1.0, r, c->fs_tu));      // t_u = x_u - A01 y_p
   int its = 0, why = 0;
@@ -212,6 +218,7 @@ static int read_solver_options(xsb_ctx c)
   if (ppc == "bjacobi" || ppc == "ilu") s.p_pc = 0; else if (ppc == "jacobi") s.p_pc = 1;
   else return xsb_fail(c, XSB_ERR_SUP, "-saddle_fieldsplit_p_pc_type %s not supported (bjacobi|ilu|jacobi)", ppc.c_str());
   s.time_kernels = o.flag("xsb_time_kernels");
+  s.mf_grad = o.integer("xsb_mf_grad", c->no_A ? 1 : 0);
   c->use_graph = o.integer("xsb_graph", 1);
   { const std::string mfv = o.str("xsb_matrix_free", "0");   // flag: fine-level products by the element kernel; "full": A / A00 never stored
     s.matrix_free = (mfv.empty() || mfv == "1" || mfv == "true" || mfv == "yes" || mfv == "full" || mfv == "2") ? 1 : 0;

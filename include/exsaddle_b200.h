@@ -47,6 +47,8 @@ enum {
   XSB_MAT_A11 = 4,  /* pressure block (stored zeros for Stokes, -1/lambda mass for LAME) */
   XSB_MAT_MP = 5,   /* scaled pressure mass matrix (MatAssemble_Schur femixedspace.c:2837) */
   XSB_MAT_A00_MF = 6, /* the velocity block applied matrix-free (sum-factorised element kernel; 3-D): xsb_mat_mult only */
+  XSB_MAT_A01_MF = 7, /* the gradient block applied by its closed-form stencil (no matrix read): xsb_mat_mult only */
+  XSB_MAT_A10_MF = 8, /* the divergence block, likewise */
   XSB_MAT_MG_LEVEL0 = 16 /* + l : Galerkin operator of PCMG level l (0 = coarsest), after xsb_ksp_setup */
 };
 
