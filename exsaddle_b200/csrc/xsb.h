@@ -209,6 +209,7 @@ struct xsb_ctx_s {
   std::vector<int> ev_cat; double prof_ms[PROF_N] = {0}; int64_t prof_cnt[PROF_N] = {0};
   int64_t a00_mode[4] = {0, 0, 0, 0};                    // fine-level A00 launches per epilogue mode
   Slab slab; void *nccl = nullptr;          // ncclComm_t when nranks > 1
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // slabs: the plane exchange of a distributed coarse level runs beside the interior rows of the product
   void *p2p = nullptr;                      // peer-memory halo windows (xsb_comm.cu), survives xsb_reset like the communicator
   Ranges own_full, own_u, own_p;            // owned entries of [u|p], u and p vectors on the local lattice
   std::vector<void *> allocs;   // every device allocation, for xsb_reset
@@ -281,7 +282,7 @@ int comm_halo_full(xsb_ctx c, double *x);         // [u|p]
 int comm_bcast_segments(xsb_ctx c, double *glob, const int64_t *offs /* nranks+1 */);
 int comm_bcast_planes(xsb_ctx c, double *glob, int64_t plane_doubles, int nplanes_glob);   // every rank contributes its owned coarse planes
 int comm_bcast_plane_ranges(xsb_ctx c, double *glob, int64_t plane_doubles, const int *p0, const int *p1);   // rank r contributes planes [p0[r], p1[r])
-int comm_halo_planes(xsb_ctx c, double *v, int64_t plane_doubles, int o0, int o1, int gb, int ga);   // ghost planes of any lattice vector (owned planes [o0,o1))
+int comm_halo_planes(xsb_ctx c, double *v, int64_t plane_doubles, int o0, int o1, int gb, int ga, cudaStream_t on = nullptr);   // ghost planes of any lattice vector (owned planes [o0,o1))
 int comm_p2p_setup(xsb_ctx c);      // collective: peer-memory windows for the halo exchange (NVLink), called by xsb_assemble
 int comm_p2p_active(xsb_ctx c);
 int comm_p2p_check(xsb_ctx c);      // sticky time-out flag of the peer-memory exchange

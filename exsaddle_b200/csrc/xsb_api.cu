@@ -84,12 +84,12 @@ int xsb_reset(xsb_ctx c)
   if (!c) return XSB_ERR_ARG;
   if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); mg_graphs_release(c); mmg_free(c); fsd_free(c); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
   Options opt = c->opt; int nsd = c->nsd, lame = c->lame, device = c->device; bool hd = c->have_device;
-  const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl, *p2p = c->p2p;
+  const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl, *p2p = c->p2p; cudaStream_t side = c->side; cudaEvent_t evf = c->ev_fork, evj = c->ev_join;
   cudaStream_t st = c->stream; cudaEvent_t e0 = c->ev0, e1 = c->ev1, k0 = c->evk0, k1 = c->evk1;
   *c = xsb_ctx_s();
   c->opt = opt; c->opt.used.clear(); c->nsd = nsd; c->lame = lame; c->device = device; c->have_device = hd;
   c->stream = st; c->ev0 = e0; c->ev1 = e1; c->evk0 = k0; c->evk1 = k1;
-  c->slab.rank = rank; c->slab.nranks = nranks; c->nccl = nccl; c->p2p = p2p;
+  c->slab.rank = rank; c->slab.nranks = nranks; c->nccl = nccl; c->p2p = p2p; c->side = side; c->ev_fork = evf; c->ev_join = evj;
   return XSB_OK;
 }
 
@@ -99,6 +99,7 @@ int xsb_destroy(xsb_ctx *pc)
   xsb_ctx c = *pc;
   xsb_reset(c);
   comm_destroy(c);
+  if (c->have_device && c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   if (c->have_device) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1); cudaStreamDestroy(c->stream); }
   delete c; *pc = nullptr;
   return XSB_OK;

@@ -65,6 +65,7 @@ int comm_init(xsb_ctx c, const void *unique_id, int rank, int nranks)
   ncclComm_t comm = nullptr;
   NCCL_OK(g_nccl.CommInitRank(&comm, nranks, id, rank));
   c->nccl = comm;
+  if (!c->side) { CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)); }
   return 0;
 }
 
@@ -204,26 +205,27 @@ void comm_p2p_destroy(xsb_ctx c) { p2p_release(c, false); }   // tear-down is no
 
 // Ghost update of a lattice vector whose planes hold `pd` doubles: this rank's owned planes are [o0,o1) in the vector's own
 // plane numbering; it needs gb planes below o0 (the top gb owned planes of rank-1) and ga planes at o1 (the bottom ga of rank+1).
-int comm_halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb, int ga)
+int comm_halo_planes(xsb_ctx c, double *v, int64_t pd, int o0, int o1, int gb, int ga, cudaStream_t on)
 {
   const Slab &S = c->slab;
   if (S.nranks == 1) return 0;
+  cudaStream_t st = on ? on : c->stream;
   const P2P *p = (const P2P *)c->p2p;
   if (p && p->on && (size_t)((gb > ga ? gb : ga) * pd) * sizeof(double) <= p->slot_bytes) {
     P2PDev w{p->ctl, p->win, p->peer_lo, p->peer_hi, p->slot_bytes};
     int64_t blocks = ((gb > ga ? gb : ga) * pd + 1023) / 1024; if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
-    k_halo_p2p<<<(unsigned)blocks, 256, 0, c->stream>>>(v, pd, o0, o1, gb, ga, w); KERNEL_OK();
+    k_halo_p2p<<<(unsigned)blocks, 256, 0, st>>>(v, pd, o0, o1, gb, ga, w); KERNEL_OK();
     return 0;
   }
   ncclComm_t comm = (ncclComm_t)c->nccl;
   NCCL_OK(g_nccl.GroupStart());
   if (S.rank > 0) {
-    NCCL_OK(g_nccl.Recv(v + (int64_t)(o0 - gb) * pd, (size_t)(gb * pd), ncclFloat64_, S.rank - 1, comm, c->stream));
-    NCCL_OK(g_nccl.Send(v + (int64_t)o0 * pd, (size_t)(ga * pd), ncclFloat64_, S.rank - 1, comm, c->stream));
+    NCCL_OK(g_nccl.Recv(v + (int64_t)(o0 - gb) * pd, (size_t)(gb * pd), ncclFloat64_, S.rank - 1, comm, st));
+    NCCL_OK(g_nccl.Send(v + (int64_t)o0 * pd, (size_t)(ga * pd), ncclFloat64_, S.rank - 1, comm, st));
   }
   if (S.rank < S.nranks - 1) {
-    NCCL_OK(g_nccl.Recv(v + (int64_t)o1 * pd, (size_t)(ga * pd), ncclFloat64_, S.rank + 1, comm, c->stream));
-    NCCL_OK(g_nccl.Send(v + (int64_t)(o1 - gb) * pd, (size_t)(gb * pd), ncclFloat64_, S.rank + 1, comm, c->stream));
+    NCCL_OK(g_nccl.Recv(v + (int64_t)o1 * pd, (size_t)(ga * pd), ncclFloat64_, S.rank + 1, comm, st));
+    NCCL_OK(g_nccl.Send(v + (int64_t)(o1 - gb) * pd, (size_t)(gb * pd), ncclFloat64_, S.rank + 1, comm, st));
   }
   NCCL_OK(g_nccl.GroupEnd());
   return 0;

@@ -6,7 +6,7 @@
 // On the uniform box mesh the entry does not depend on the coefficient and separates over the directions:
 //     A01[(n_u, c), n_p] = - prod_d T_d ,   T_d = G_d[i_d][P_d] (d == c)  or  M_d[i_d][P_d] (d != c)
 //     M_d[l][m] = sum_q w_q b_l(xi_q) psi_m(xi_q) h_d ,   G_d[l][m] = sum_q w_q b'_l(xi_q) psi_m(xi_q)     (1-D Q2 x Q1 element tables)
-// summed over the (one or two) elements that contain both nodes -- checked against the assembled blocks of the oracle to 1e-15
+// summed over the (one or two) elements that contain both nodes -- equal to the assembled blocks to 1e-15 (tests/test_gpu_parity.py)
 // for Stokes and Lame, 2-D / 3-D, non-unit box sizes.  So the products stream x and y once and no matrix: 0.1 GB instead of
 // 2.4 GB of CSR traffic per outer iteration at 64^3, and A01 / A10 need not be read at all during the solve.
 //   k_grad: one thread per velocity node, <= 27 pressure values, all NSD components at once;

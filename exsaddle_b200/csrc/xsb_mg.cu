@@ -374,6 +374,19 @@ static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, doubl
   // plane-distributed level: this rank computes the rows of its node planes (rows and fused epilogue are per row, so the
   // values are bitwise those of the one-GPU product) and trades one plane of the result with each neighbour
   const int pn = L.nx * L.ny;
+  if (c->side && L.rp1 - L.rp0 >= 4 && c->opt.integer("xsb_overlap", 1)) {
+    // the two planes the neighbours need first; their exchange (a synchronisation point with both neighbours) then runs on a
+    // second stream beside the interior rows -- fork / join by events, so the pattern is captured into the V-cycle graphs as is
+    XSB_CHK(spmv_baij(c, L.A, x, y, ep, L.rp0 * pn, pn));
+    XSB_CHK(spmv_baij(c, L.A, x, y, ep, (L.rp1 - 1) * pn, pn));
+    CUDA_OK(cudaEventRecord(c->ev_fork, c->stream)); CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    XSB_CHK(comm_halo_planes(c, y, (int64_t)L.A.bs * pn, L.rp0, L.rp1, 1, 1, c->side));
+    CUDA_OK(cudaEventRecord(c->ev_join, c->side));
+    XSB_CHK(spmv_baij(c, L.A, x, y, ep, (L.rp0 + 1) * pn, (L.rp1 - L.rp0 - 2) * pn));
+    XSB_CHK(prof_mark(c, PROF_CHALO));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    return prof_mark(c, PROF_OTHER);
+  }
   XSB_CHK(spmv_baij(c, L.A, x, y, ep, L.rp0 * pn, (L.rp1 - L.rp0) * pn));
   XSB_CHK(prof_mark(c, PROF_CHALO));
   XSB_CHK(comm_halo_planes(c, y, (int64_t)L.A.bs * pn, L.rp0, L.rp1, 1, 1));
