@@ -41,7 +41,8 @@ ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iterations.json")
 
 
 def workload_options(a):
-    return "%s -saddle_fieldsplit_u_pc_mg_levels %d -model 6 -mx %d -eta0 1 -eta1 %g -saddle_ksp_rtol 1e-8" % (ABF, a.levels, a.mx, a.eta1)
+    extra = os.environ.get("XSB_BENCH_EXTRA_OPTS", "")   # experiments only (library tuning switches); printed with the options in `config`
+    return "%s -saddle_fieldsplit_u_pc_mg_levels %d -model 6 -mx %d -eta0 1 -eta1 %g -saddle_ksp_rtol 1e-8%s" % (ABF, a.levels, a.mx, a.eta1, (" " + extra) if extra else "")
 
 
 # measured once per kernel change with `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum per launch), see profiles/

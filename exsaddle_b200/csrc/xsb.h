@@ -240,6 +240,7 @@ enum { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_CHEB_FIRST = 2, EPI_CHEB = 3 };
 struct Epilogue { int mode = EPI_PLAIN; const double *b = nullptr, *idiag = nullptr, *pk = nullptr, *pkm1 = nullptr; double s0 = 0, s1 = 0, s2 = 0; };
 int spmv_csr(xsb_ctx c, const Csr &A, const double *x, double *y, int64_t row0 = 0, int64_t nrows = -1, const double *yadd = nullptr);   // y = A x (+ yadd)
 int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0 = 0, int nnodes = -1);
+int spmv_baij_pair(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int nodeA, int nodeB, int nnodes);   // two row ranges, one launch
 int spmv_a00_fine(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep);   // counted (+ timed) fine-level launch
 int spmv_collect_timing(xsb_ctx c);
 int prof_mark(xsb_ctx c, int cat);   // -xsb_time_kernels: the time from here to the next mark belongs to category `cat`

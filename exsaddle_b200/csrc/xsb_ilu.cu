@@ -280,6 +280,9 @@ __device__ __forceinline__ void ilup_sweep(const IluPipe P, const int kb, const 
   double *xown = out + ridx(0, line ? jb : 0, kb);
   const double *rown = rhs + ridx(0, line ? jb : 0, kb);
   const bool v0 = line && kb > 0 && jb > 0, v1 = line && kb > 0, v2 = line && kb > 0 && jb + 1 < P.py;
+  double2 *rows_t = rows + (size_t)t * 7; const int slot_stride = 7 * T;   // factor ring [slot][thread][7 x 16 B]: a thread's record is contiguous (pitch 112 B: conflict-free for 128-bit accesses)
+  double *xs_me = xs + t * 4; const double *xs_lo = xs + (t > 0 ? t - 1 : 0) * 4;
+  static_assert(ILUP_PF == ILUP_D + 1 && ILUP_PF == 4, "ring slots are derived from the unroll index");
   for (int s0 = -2 * ILUP_PF; s0 < P.S; s0 += ILUP_PF) {
 #pragma unroll
     for (int u = 0; u < ILUP_PF; ++u) {
@@ -305,29 +308,28 @@ __device__ __forceinline__ void ilup_sweep(const IluPipe P, const int kb, const 
         const bool rv = line && ib8 >= 0 && ib8 < P.px;
         ring[u][3] = rv ? (BWD ? __ldcg(rown + dx * ib8) : __ldg(rown + dx * ib8)) : 0.0;
       }
-      {   // factor record of step s + ILUP_D -> shared memory; of step s + 32 -> L2
+      {   // factor record of step s + ILUP_D -> shared memory (1.8 us ahead: covers the DRAM latency, no separate L2 prefetch)
         const int sr = s + ILUP_D, ir = sr - 2 * jb;
         if (line && ir >= 0 && ir < P.px) {
           const double *rec = pk + (sr * P.W + (jb - ilup_jlo(sr, P.px))) * 16;
-          double2 *dst = rows + (size_t)((sr & ILUP_D) * 7) * T + t;
+          double2 *dst = rows_t + ((u + ILUP_D) & ILUP_D) * slot_stride;   // slot of step s + ILUP_D: s0 is a multiple of the ring size, so it is known at compile time
 #pragma unroll
-          for (int cc = 0; cc < 7; ++cc) cp_async16(dst + (size_t)cc * T, rec + 2 * cc);
+          for (int cc = 0; cc < 7; ++cc) cp_async16(dst + cc, rec + 2 * cc);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const int sp = s + 32, ip = sp - 2 * jb;
-        if (line && ip >= 0 && ip < P.px) prefetch_l2(pk + (sp * P.W + (jb - ilup_jlo(sp, P.px))) * 16);
       }
       if (s >= 0 && s < P.S) {
         asm volatile("cp.async.wait_group %0;" :: "n"(ILUP_D) : "memory");
         if (line && ib >= 0 && ib < P.px) {
-          const double2 *src = rows + (size_t)((s & ILUP_D) * 7) * T + t;
+          const double2 *src = rows_t + (u & ILUP_D) * slot_stride;
           double L[14];
 #pragma unroll
-          for (int cc = 0; cc < 7; ++cc) { const double2 v = src[(size_t)cc * T]; L[2 * cc] = v.x; L[2 * cc + 1] = v.y; }
+          for (int cc = 0; cc < 7; ++cc) { const double2 v = src[cc]; L[2 * cc] = v.x; L[2 * cc + 1] = v.y; }
           const bool jm = jb > 0;
-          const double q0 = (jm && ib > 0) ? xs[(t - 1) * 4 + ((ib - 1) & 3)] : 0.0;
-          const double q1 = jm ? xs[(t - 1) * 4 + (ib & 3)] : 0.0;
-          const double q2 = (jm && ib + 1 < P.px) ? xs[(t - 1) * 4 + ((ib + 1) & 3)] : 0.0;
+          // line jb-1 is two nodes ahead: its positions ib-1, ib, ib+1 were its steps s-3, s-2, s-1 (ring slot = step mod 4, static)
+          const double q0 = (jm && ib > 0) ? xs_lo[(u + 1) & 3] : 0.0;
+          const double q1 = jm ? xs_lo[(u + 2) & 3] : 0.0;
+          const double q2 = (jm && ib + 1 < P.px) ? xs_lo[(u + 3) & 3] : 0.0;
           double acc = rhs_now;
           acc -= L[0] * w[0][0]; acc -= L[1] * w[0][1]; acc -= L[2] * w[0][2];
           acc -= L[3] * w[1][0]; acc -= L[4] * w[1][1]; acc -= L[5] * w[1][2];
@@ -336,7 +338,7 @@ __device__ __forceinline__ void ilup_sweep(const IluPipe P, const int kb, const 
           acc -= L[12] * xprev;
           if (BWD) acc *= L[13];
           st_relaxed_gpu_f64(xown + dx * ib, acc);
-          xs[t * 4 + (ib & 3)] = acc; xprev = acc;
+          xs_me[u & 3] = acc; xprev = acc;
         }
       }
       __syncthreads();

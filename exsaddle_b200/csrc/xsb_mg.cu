@@ -377,8 +377,7 @@ static int a00_spmv(xsb_ctx c, const Level &L, bool fine, const double *x, doubl
   if (c->side && L.rp1 - L.rp0 >= 4 && c->opt.integer("xsb_overlap", 1)) {
     // the two planes the neighbours need first; their exchange (a synchronisation point with both neighbours) then runs on a
     // second stream beside the interior rows -- fork / join by events, so the pattern is captured into the V-cycle graphs as is
-    XSB_CHK(spmv_baij(c, L.A, x, y, ep, L.rp0 * pn, pn));
-    XSB_CHK(spmv_baij(c, L.A, x, y, ep, (L.rp1 - 1) * pn, pn));
+    XSB_CHK(spmv_baij_pair(c, L.A, x, y, ep, L.rp0 * pn, (L.rp1 - 1) * pn, pn));
     CUDA_OK(cudaEventRecord(c->ev_fork, c->stream)); CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     XSB_CHK(comm_halo_planes(c, y, (int64_t)L.A.bs * pn, L.rp0, L.rp1, 1, 1, c->side));
     CUDA_OK(cudaEventRecord(c->ev_join, c->side));

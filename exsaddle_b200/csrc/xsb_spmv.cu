@@ -195,6 +195,54 @@ __global__ void __launch_bounds__(256) spmv_baij_kernel(int node0, int nb, const
   }
 }
 
+// The same product for TWO row ranges of equal length in one launch (blockIdx.y picks the range): the two boundary planes of a
+// plane-distributed coarse level, whose results the neighbours wait for (xsb_mg.cu).  Kept as a separate kernel on purpose.
+template <int BS, int UN>
+__global__ void __launch_bounds__(256) spmv_baij_pair_kernel(int nodeA, int nodeB, int nb, const int *__restrict__ ia, const int *__restrict__ ja,
+                                                             const double *__restrict__ a, const double *__restrict__ x, double *__restrict__ y, Epilogue ep)
+{
+  constexpr int BS2 = BS * BS, NBW = 32 / BS2, ACTIVE = NBW * BS2;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / BS2, r = lane - g * BS2, ra = r / BS, ca = r - ra * BS;
+  const bool active = lane < ACTIVE;
+  const int node0 = blockIdx.y ? nodeB : nodeA;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t node = node0 + warp; node < node0 + nb; node += nwarps) {
+    const int b0 = ia[node], nblk = ia[node + 1] - b0;
+    const double *__restrict__ av = a + (int64_t)b0 * BS2 + lane;
+    const int *__restrict__ cj = ja + b0 + g;
+    const int mine = active ? (nblk - g + NBW - 1) / NBW : 0;
+    double acc = 0.0;
+    for (int it = 0; it < mine; it += UN) {
+      double v[UN]; int col[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const bool ok = it + u < mine;
+        v[u] = ok ? ld_stream(av + (int64_t)(it + u) * ACTIVE) : 0.0;
+        col[u] = ok ? __ldg(cj + (it + u) * NBW) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) acc += v[u] * __ldg(x + (int64_t)BS * col[u] + ca);
+    }
+    double t = acc;
+#pragma unroll
+    for (int s = 1; s < BS; ++s) t += __shfl_down_sync(0xffffffffu, acc, s);
+    double tot = t;
+#pragma unroll
+    for (int s = 1; s < NBW; ++s) tot += __shfl_down_sync(0xffffffffu, t, s * BS2);
+    if (g == 0 && ca == 0 && active) { const int64_t i = (int64_t)BS * node + ra; y[i] = epilogue_value(ep, i, tot); }
+  }
+}
+int spmv_baij_pair(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int nodeA, int nodeB, int nnodes)
+{
+  if (nnodes <= 0) return XSB_OK;
+  if (A.bs != 3) { XSB_CHK(spmv_baij(c, A, x, y, ep, nodeA, nnodes)); return spmv_baij(c, A, x, y, ep, nodeB, nnodes); }
+  const int tpb = 256; dim3 grid((unsigned)(((int64_t)nnodes * 32 + tpb - 1) / tpb), 2);
+  spmv_baij_pair_kernel<3, 8><<<grid, tpb, 0, c->stream>>>(nodeA, nodeB, nnodes, A.ia, A.ja, A.a, x, y, ep);
+  KERNEL_OK();
+  return XSB_OK;
+}
+
 int spmv_baij(xsb_ctx c, const Baij &A, const double *x, double *y, const Epilogue &ep, int node0, int nnodes)
 {
   if (nnodes < 0) nnodes = A.nb - node0;
