@@ -217,6 +217,7 @@ struct xsb_ctx_s {
   void *fe_tables = nullptr;    // FeTables on the device
   void *mmg = nullptr;          // monolithic -mg hierarchy (xsb_mmg.cu)
   void *asmpc = nullptr;        // -saddle_pc_type asm (xsb_asm.cu)
+  void *grad_tab = nullptr; int grad_key[3] = {0, 0, 0};   // per-direction coefficient tables of the gradient / divergence stencils (xsb_grad.cu)
   void *fsd = nullptr;          // default -fs tree: GMRES + ILU(0) sub-solvers (xsb_fs.cu)
   const double *nodal_in = nullptr;   // coarse -mg level: nodal Q1 coefficient fields [slot][p-node] to use instead of the model
 };
@@ -306,6 +307,8 @@ void mmg_free(xsb_ctx c);
 // ---- xsb_grad.cu (gradient / divergence blocks matrix-free)
 int grad_apply(xsb_ctx c, const double *xp, double *y, int64_t dof0, int64_t ndofs, const double *yadd = nullptr);   // y_u rows = A01 xp (+ yadd)
 int div_apply(xsb_ctx c, const double *xu, double *y, int64_t p0, int64_t np, const double *yadd = nullptr);         // y_p rows = A10 xu (+ yadd)
+void grad_free(xsb_ctx c);
+int grad_prepare(xsb_ctx c);   // coefficient tables of the current lattice (idempotent)
 // ---- xsb_asm.cu (additive Schwarz on the reference's element patches)
 int asm_setup(xsb_ctx alloc, xsb_ctx problem, int size, int overlap, void **out);
 int asm_apply(xsb_ctx c, void *asmpc, const double *r, double *z);

@@ -82,7 +82,7 @@ int xsb_create(xsb_ctx *out, int nsd, int lame, int device)
 int xsb_reset(xsb_ctx c)
 {
   if (!c) return XSB_ERR_ARG;
-  if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); mg_graphs_release(c); mmg_free(c); fsd_free(c); dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
+  if (c->have_device) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); mg_graphs_release(c); mmg_free(c); fsd_free(c); grad_free(c); if (c->asmpc) { asm_free(c->asmpc); c->asmpc = nullptr; } dev_free_all(c); if (c->red_h) cudaFreeHost(c->red_h); for (cudaEvent_t e : c->evpool) cudaEventDestroy(e); }
   Options opt = c->opt; int nsd = c->nsd, lame = c->lame, device = c->device; bool hd = c->have_device;
   const int rank = c->slab.rank, nranks = c->slab.nranks; void *nccl = c->nccl, *p2p = c->p2p; cudaStream_t side = c->side; cudaEvent_t evf = c->ev_fork, evj = c->ev_join;
   cudaStream_t st = c->stream; cudaEvent_t e0 = c->ev0, e1 = c->ev1, k0 = c->evk0, k1 = c->evk1;

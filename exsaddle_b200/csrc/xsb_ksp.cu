@@ -271,6 +271,7 @@ int ksp_setup(xsb_ctx c)
   if (c->so.pc_type == 5) XSB_CHK(asm_setup(c, c, c->opt.integer("xsb_ranks", 1), c->opt.integer("dmdafe_overlap", 0), &c->asmpc));
   if (c->so.pc_type == 2) {
     if (c->so.matrix_free) XSB_CHK(mf_setup(c));
+    if (c->so.mf_grad) XSB_CHK(grad_prepare(c));
     XSB_CHK(mg_setup(c));
     if (c->so.p_pc == 0) XSB_CHK(ilu_setup(c));
     else { XSB_CHK(dev_alloc(c, &c->mp_idiag, (size_t)L.np)); XSB_CHK(csr_diag_inv(c, c->Mp, c->mp_idiag)); }
