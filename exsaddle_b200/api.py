@@ -62,6 +62,7 @@ def lib():
             "xsb_prealloc_total": [C.c_int, C.c_int, C.c_int, C.c_int],
             "xsb_bc_list": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, dp, C.c_int],
             "xsb_mg_level_dims": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
+            "xsb_grad_line_tables": [C.c_int, C.c_double, i32p, dp, dp, dp, dp],
             "xsb_dmda_grid": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
             "xsb_asm_subdomain": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)],
             "xsb_slab_range": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
@@ -125,6 +126,16 @@ def slab_range(mz, nranks, rank):
     if rc:
         raise XsbError(rc, "bad slab request")
     return a.value, b.value
+
+
+def grad_line_tables(m, h):
+    """per-direction coefficient tables of the matrix-free gradient / divergence blocks (xsb_grad_line_tables)"""
+    import numpy as np
+    uP = np.empty(3 * (2 * m + 1), np.int32); uM = np.empty(3 * (2 * m + 1)); uG = np.empty_like(uM); pM = np.empty(5 * (m + 1)); pG = np.empty_like(pM)
+    rc = lib().xsb_grad_line_tables(m, h, uP.ctypes.data_as(C.POINTER(C.c_int32)), _dp(uM), _dp(uG), _dp(pM), _dp(pG))
+    if rc:
+        raise XsbError(rc, "bad table request")
+    return uP.reshape(-1, 3), uM.reshape(-1, 3), uG.reshape(-1, 3), pM.reshape(-1, 5), pG.reshape(-1, 5)
 
 
 def dmda_grid(nsd, M, N, P, size):

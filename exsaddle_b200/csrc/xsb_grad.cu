@@ -128,6 +128,20 @@ static void line_tables(int m, const double (*M)[2], const double (*G)[2], std::
     for (int a = 0; a < 3; ++a) if (uP[3 * i + a] == Pn) { pM[5 * Pn + di] = uM[3 * i + a]; pG[5 * Pn + di] = uG[3 * i + a]; }
   }
 }
+// host-only view of the tables of one direction (m elements, node spacing h), for the CPU tests: uP/uM/uG hold 3 entries per
+// velocity node, pM/pG 5 entries per pressure node
+extern "C" int xsb_grad_line_tables(int m, double h, int32_t *uP, double *uM, double *uG, double *pM, double *pG)
+{
+  if (m < 1 || !(h > 0.0) || !uP || !uM || !uG || !pM || !pG) return XSB_ERR_ARG;
+  Lattice L{}; L.hu[0] = L.hu[1] = L.hu[2] = h;
+  GradTab T; grad_tables(L, T);
+  std::vector<int> a; std::vector<double> b, c, d, e;
+  line_tables(m, T.M[0], T.G[0], a, b, c, d, e);
+  for (size_t i = 0; i < a.size(); ++i) { uP[i] = a[i]; uM[i] = b[i]; uG[i] = c[i]; }
+  for (size_t i = 0; i < d.size(); ++i) { pM[i] = d[i]; pG[i] = e[i]; }
+  return XSB_OK;
+}
+
 int grad_prepare(xsb_ctx c)
 {
   const Lattice &L = c->lat;

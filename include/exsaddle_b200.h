@@ -165,6 +165,14 @@ int xsb_bc_list(int nsd, int lame, int model, int freeslip, int mx, int my, int 
 /* PCMG level lattice: DMCoarsen n -> (n-1)/2+1; returns 0 or XSB_ERR_ARG when not coarsenable */
 int xsb_mg_level_dims(int nsd, int mx, int my, int mz, int levels, int level, int dims[3]);
 
+/* -------- gradient / divergence blocks without a matrix (csrc/xsb_grad.cu) ----------------------------------- */
+/* host-only: the per-direction coefficient tables behind XSB_MAT_A01_MF / XSB_MAT_A10_MF for a line of m elements with node
+   spacing h.  Velocity node i couples to the pressure nodes uP[3i..3i+2] (-1 = none) with the 1-D mass-type factors uM and
+   derivative-type factors uG (sums of the Q2 x Q1 element-table entries over the elements containing both nodes); pM / pG hold the
+   same numbers seen from pressure node P: its velocity nodes 2P-2 .. 2P+2.  An entry of A01 (MatAssemble_Saddle,
+   femixedspace.c:2576-2579) is minus the product over the directions, G-type in the component's own direction. */
+int xsb_grad_line_tables(int m, double h, int32_t *uP, double *uM, double *uG, double *pM, double *pG);
+
 /* -------- ASM on the reference's element patches --------------------------------------- */
 /* Process grid PETSc's DMDACreate{2,3}d(PETSC_DECIDE) picks for M x N (x P) nodes on `size` ranks (the velocity DMDA of
    femixedspace.c:1153-1158); XSB_ERR_ARG when `size` cannot be factored onto the lattice. */

@@ -210,3 +210,46 @@ def test_bench_reference_arm_other_ranks_exit_without_work():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], cwd=ROOT, env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("nsd,lame,opts", [(3, False, "-model 6 -mx 4 -my 3 -mz 2 -eta1 100"), (2, False, "-model 0 -mx 5 -my 3 -size_x 2.0"), (3, True, "-model 6 -mx 3 -mu1 10 -lambda1 5")])
+def test_gradient_block_from_the_products_1d_tables_equals_the_oracles_assembled_block(nsd, lame, opts):
+    """The tables behind the matrix-free gradient / divergence products (host code of the library, no GPU): A01 rebuilt from them as a
+    sum of Kronecker products equals the oracle's assembled A[u,p] to 1e-14 (constrained rows removed on both sides), and the
+    pressure-side tables are the transpose view of the velocity-side ones."""
+    import scipy.sparse as sp
+    from oracle import oracle as O
+    p = O.Problem(opts, nsd=nsd, lame=lame); o = O.parse_options(opts)
+    mx = int(o.get("mx", 4)); mesh = [mx, int(o.get("my", mx)), int(o.get("mz", mx))][:nsd]
+    size = [float(o.get("size_" + "xyz"[d], 1.0)) for d in range(nsd)]
+    nu = p.nu; A01 = p.A().scipy().tocsr()[:nu, nu:]
+    fac = []
+    for d in range(nsd):
+        uP, uM, uG, pM, pG = X.grad_line_tables(mesh[d], size[d] / (2 * mesh[d]))
+        N, P = 2 * mesh[d] + 1, mesh[d] + 1
+        M = np.zeros((N, P)); G = np.zeros((N, P))
+        for i in range(N):
+            for a in range(3):
+                if uP[i, a] >= 0:
+                    M[i, uP[i, a]] += uM[i, a]; G[i, uP[i, a]] += uG[i, a]
+        for Pn in range(P):            # the divergence kernel's view of the same numbers
+            for di in range(5):
+                i = 2 * Pn - 2 + di
+                assert (pM[Pn, di], pG[Pn, di]) == ((M[i, Pn], G[i, Pn]) if 0 <= i < N else (0.0, 0.0))
+        fac.append((sp.csr_matrix(M), sp.csr_matrix(G)))
+    blocks = []
+    for c in range(nsd):               # component c: derivative factor in its own direction; node index = i + NX (j + NY k): kron(z, y, x)
+        K = None
+        for d in reversed(range(nsd)):
+            f = fac[d][1] if d == c else fac[d][0]
+            K = f if K is None else sp.kron(K, f, format="csr")
+        blocks.append(-K)
+    n_nodes = blocks[0].shape[0]
+    B = sp.lil_matrix((nu, A01.shape[1]))
+    rows = np.arange(n_nodes) * nsd
+    B = sp.vstack([blk for blk in blocks]).tocsr()                      # rows grouped by component ...
+    perm = np.concatenate([np.arange(n_nodes) + c * n_nodes for c in range(nsd)]).reshape(nsd, n_nodes).T.ravel()
+    B = B[perm]                                                           # ... back to node-major, component-fastest order
+    bi, _ = p.bc(); keep = np.ones(nu, bool); keep[bi[bi < nu]] = False
+    D = (sp.diags(keep.astype(float)) @ B - A01).tocoo()
+    assert np.max(np.abs(D.data), initial=0.0) <= 1e-14 * np.max(np.abs(A01.data))
