@@ -7,6 +7,7 @@ import json
 import os
 
 import numpy as np
+import scipy.sparse as sp
 import pytest
 
 from oracle import oracle as O
@@ -379,6 +380,89 @@ def test_wavefront_window_of_the_pressure_ilu_sweeps():
             s = s * d                                        # the factor stores 1 / pivot (xo_ilu0)
             ring[(lvl & 7) * maxw + pos[r]] = s; x[r] = s
     assert not np.isnan(x).any() and np.linalg.norm(x - xs) <= 1e-13 * np.linalg.norm(xs)
+
+
+@pytest.mark.parametrize("mesh", [(6, 5, 4), (3, 7, 2), (5, 2, 6)])
+def test_line_pipelined_schedule_of_the_pressure_ilu_sweeps(mesh):
+    """Claim behind the default ILU(0) solve kernel (k_ilup_solve, xsb_ilu.cu), emulated on the oracle's factors with the kernel's data
+    flow: one "CTA" per node plane, one "thread" per node line; at in-plane step t thread j handles node i = t - 2j using ONLY
+      * its own previous value (a register),
+      * the values line j-1 produced at steps t-3, t-2, t-1, read from a 4-slot ring indexed by step (positions i-1, i, i+1),
+      * values of the plane below that were produced at in-plane steps <= t + 3 -- so a plane may run as soon as the plane below is four
+        steps ahead (the kernel additionally fetches them four steps early), with the sentinel marking what has not been written;
+    the factors come from one 13-entry record per row in sweep order, zero where the lattice ends; the backward sweep is the forward
+    sweep on the mirrored lattice.  The emulation advances all planes in lock-step with the minimal lag and must meet no sentinel; the
+    result equals the sequential MatSolve."""
+    mx, my, mz = mesh
+    o = O.Problem("-model 6 -mx %d -my %d -mz %d -eta1 100" % mesh, nsd=3)
+    M = o.Mp(); n = o.np_
+    lu = np.empty_like(M.a)
+    assert O.lib().xo_ilu0(n, O._ip(M.ia), O._ip(M.ja), O._dp(M.a), O._dp(lu)) == 0
+    px, py, pz = mx + 1, my + 1, mz + 1
+    A = sp.csr_matrix((lu, M.ja, M.ia), shape=(n, n)).tocsr()
+    rng = np.random.default_rng(1); b = rng.standard_normal(n)
+    xs = np.empty(n); O.lib().xo_ilu0_solve(n, O._ip(M.ia), O._ip(M.ja), O._dp(lu), O._dp(b), O._dp(xs))
+    offs = [(u % 3 - 1, (u // 3) % 3 - 1, -1) for u in range(9)] + [(-1, -1, 0), (0, -1, 0), (1, -1, 0), (-1, 0, 0)]   # sweep order of the 13 earlier neighbours
+
+    def sweep(rhs, bwd):
+        real = (lambda i, j, k: (px - 1 - i, py - 1 - j, pz - 1 - k)) if bwd else (lambda i, j, k: (i, j, k))
+        idx = lambda i, j, k: i + px * (j + py * k)
+        rec = {}                                   # packed records: mirrored row -> 13 factors (+ 1 / pivot)
+        for k in range(pz):
+            for j in range(py):
+                for i in range(px):
+                    r = idx(*real(i, j, k)); L = np.zeros(14)
+                    for u, (di, dj, dk) in enumerate(offs):
+                        ni, nj, nk = i + di, j + dj, k + dk
+                        if 0 <= ni < px and 0 <= nj < py and 0 <= nk < pz:
+                            L[u] = A[r, idx(*real(ni, nj, nk))]
+                    L[13] = A[r, r]
+                    rec[(i, j, k)] = L
+        SENT = object()
+        out = {}                                   # (i, j, k) mirrored -> value; absent = sentinel
+        S = px + 2 * (py - 1); lag = 4
+        ring = np.zeros((pz, py, 4)); xprev = np.zeros((pz, py))
+        for T in range(S + lag * (pz - 1)):        # global clock; plane k runs its in-plane step t = T - lag k
+            for k in range(pz):
+                t = T - lag * k
+                if not 0 <= t < S:
+                    continue
+                new = {}
+                for j in range(py):
+                    i = t - 2 * j
+                    if not 0 <= i < px:
+                        continue
+                    L = rec[(i, j, k)]
+                    xv = []
+                    for (di, dj, dk) in offs[:9]:  # plane below: must already be there (produced at in-plane step <= t + 3 of plane k-1, i.e. clock <= T - 1)
+                        key = (i + di, j + dj, k - 1)
+                        if k == 0 or not (0 <= key[0] < px and 0 <= key[1] < py):
+                            xv.append(0.0)
+                        else:
+                            assert key in out, ("sentinel met: the plane below is not far enough ahead", T, k, j, i)
+                            assert key[0] + 2 * key[1] <= t + 3
+                            xv.append(out[key])
+                    for di in (-1, 0, 1):          # line j-1 through the step-indexed ring: slots (t-3, t-2, t-1) & 3
+                        ok = j > 0 and 0 <= i + di < px
+                        xv.append(ring[k, j - 1, (t - 2 + di) & 3] if ok else 0.0)
+                    xv.append(xprev[k, j] if i > 0 else 0.0)
+                    acc = rhs[idx(*real(i, j, k))]
+                    for u in range(13):
+                        acc -= L[u] * xv[u]
+                    if bwd:
+                        acc *= L[13]
+                    new[j] = (i, acc)
+                for j, (i, acc) in new.items():    # the block barrier: writes of step t become visible to step t + 1
+                    ring[k, j, t & 3] = acc; xprev[k, j] = acc; out[(i, j, k)] = acc
+        res = np.empty(n)
+        for (i, j, k), v in out.items():
+            res[idx(*real(i, j, k))] = v
+        assert len(out) == n
+        return res
+
+    y = sweep(b, False)
+    x = sweep(y, True)
+    assert np.linalg.norm(x - xs) <= 1e-13 * np.linalg.norm(xs)
 
 
 def test_monolithic_mg_fs_coarse_golden(kat):
