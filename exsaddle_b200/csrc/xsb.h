@@ -190,6 +190,7 @@ struct xsb_ctx_s {
   struct VGraph { const double *b = nullptr; double *x = nullptr, *w0 = nullptr, *w1 = nullptr; cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr;
                   int64_t d_a00 = 0, d_launch = 0, d_mode[4] = {0, 0, 0, 0}; double *px[XSB_MAX_LEVELS], *pw0[XSB_MAX_LEVELS], *pw1[XSB_MAX_LEVELS]; };
   std::vector<VGraph> vgraphs; int use_graph = 1; int64_t graph_replays = 0;
+  double *mp_block_a = nullptr;   // values of Mpscaled with the entries between different ranks' dofs zeroed (plain -fs tree with -xsb_ranks > 1)
   double *mp_lu = nullptr, *mp_idiag = nullptr; int *ilu_rows = nullptr, *ilu_lvl_off = nullptr, *ilu_diag = nullptr; int ilu_nlvl = 0;
   int *ilu_fcol = nullptr, *ilu_bcol = nullptr; double *ilu_fval = nullptr, *ilu_bval = nullptr, *ilu_binv = nullptr; unsigned char *ilu_fn = nullptr, *ilu_bn = nullptr;
   std::vector<int> ilu_lvl_off_h;

@@ -306,6 +306,42 @@ int fsc_solve(xsb_ctx c, void *h, const double *b, double *x)
 }
 int fsc_last_its(void *h) { FsCoarse *F = (FsCoarse *)h; return F->its.empty() ? 0 : F->its.back(); }
 
+// bjacobi on R ranks (goldens *_fs_2): entries that couple dofs of different ranks are zeroed in the copies the ILU(0)s factor.
+// ILU(0) of such a matrix in natural ordering IS the block ILU(0) (cross-block entries stay exactly zero through the elimination,
+// in-block operations and their order are those of the rank-local factorisation: ownership is a box, so the rank-local DMDA
+// ordering is the natural ordering restricted to the box).
+__global__ void k_zero_cross_block(int n, const int *__restrict__ ia, const int *__restrict__ ja, double *__restrict__ a, const int *__restrict__ owner)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x; if (row >= n) return;
+  const int o = owner[row];
+  for (int k = ia[row]; k < ia[row + 1]; ++k) if (owner[ja[k]] != o) a[k] = 0.0;
+}
+// owner rank of every velocity dof / pressure node for the communicator size R (xsb_asm_subdomain: PETSc's DMDA ownership)
+static int rank_owners(xsb_ctx c, int R, int **own_u, int **own_p)
+{
+  const Lattice &L = c->lat; const int nsd = L.nsd;
+  std::vector<int> hu(L.nu, -1), hp(L.np, -1);
+  for (int r = 0; r < R; ++r) {
+    int b[18];
+    if (xsb_asm_subdomain(nsd, L.mx, L.my, L.mz, R, 0, r, b)) return xsb_fail(c, XSB_ERR_ARG, "-xsb_ranks %d: PETSc's DMDA cannot partition this mesh into whole Q2 elements", R);
+    for (int k = nsd == 3 ? b[8] : 0; k < (nsd == 3 ? b[11] : 1); ++k) for (int j = b[7]; j < b[10]; ++j) for (int i = b[6]; i < b[9]; ++i) {
+      const int64_t nd = i + (int64_t)j * L.NX + (int64_t)k * L.NX * L.NY;
+      for (int d = 0; d < nsd; ++d) hu[nd * nsd + d] = r;
+    }
+    for (int k = nsd == 3 ? b[14] : 0; k < (nsd == 3 ? b[17] : 1); ++k) for (int j = b[13]; j < b[16]; ++j) for (int i = b[12]; i < b[15]; ++i)
+      hp[i + (int64_t)j * L.PX + (int64_t)k * L.PX * L.PY] = r;
+  }
+  for (int v : hu) if (v < 0) return xsb_fail(c, XSB_ERR_ARG, "rank ownership does not cover the velocity lattice");
+  for (int v : hp) if (v < 0) return xsb_fail(c, XSB_ERR_ARG, "rank ownership does not cover the pressure lattice");
+  XSB_CHK(dev_alloc(c, own_u, (size_t)L.nu)); XSB_CHK(dev_alloc(c, own_p, (size_t)L.np));
+  // on the handle's (non-blocking) stream, and waited for: a blocking cudaMemcpy from pageable memory may return before its DMA
+  // has landed, and nothing orders the legacy stream against the kernels that read these arrays
+  CUDA_OK(cudaMemcpyAsync(*own_u, hu.data(), sizeof(int) * L.nu, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(*own_p, hp.data(), sizeof(int) * L.np, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 void fsd_free(xsb_ctx c) { if (c->fsd) { delete (Fsd *)c->fsd; c->fsd = nullptr; } }
 
 int fsd_setup(xsb_ctx c)
@@ -328,8 +364,18 @@ int fsd_setup(xsb_ctx c)
   if (bs == 3) k_baij_scalar<3><<<(B.nb + 256) / 256, 256, 0, st>>>(B.nb, B.ia, B.ja, B.a, S.ia, S.ja, S.a);
   else k_baij_scalar<2><<<(B.nb + 256) / 256, 256, 0, st>>>(B.nb, B.ia, B.ja, B.a, S.ia, S.ja, S.a);
   KERNEL_OK();
+  c->mp_block_a = nullptr;
+  const int R = o.integer("xsb_ranks", 1);
+  if (R > 1) {   // the reference on R ranks: PETSc's default inner PC is bjacobi, one ILU(0) block per rank
+    int *own_u = nullptr, *own_p = nullptr;
+    XSB_CHK(rank_owners(c, R, &own_u, &own_p));
+    k_zero_cross_block<<<(S.n + 255) / 256, 256, 0, st>>>(S.n, S.ia, S.ja, S.a, own_u); KERNEL_OK();
+    XSB_CHK(dev_alloc(c, &c->mp_block_a, (size_t)c->Mp.nnz));
+    CUDA_OK(cudaMemcpyAsync(c->mp_block_a, c->Mp.a, sizeof(double) * c->Mp.nnz, cudaMemcpyDeviceToDevice, st));
+    k_zero_cross_block<<<(c->Mp.n + 255) / 256, 256, 0, st>>>(c->Mp.n, c->Mp.ia, c->Mp.ja, c->mp_block_a, own_p); KERNEL_OK();
+  }
   XSB_CHK(gilu_setup(c, S, F->ilu_u));
-  XSB_CHK(ilu_setup(c));   // ILU(0) of Mpscaled (lattice wavefronts, xsb_ilu.cu)
+  XSB_CHK(ilu_setup(c));   // ILU(0) of Mpscaled (xsb_ilu.cu); of its rank-block-diagonal part when -xsb_ranks > 1
   XSB_CHK(dev_alloc(c, &F->u_t1, (size_t)L.nu)); XSB_CHK(dev_alloc(c, &F->u_t2, (size_t)L.nu)); XSB_CHK(dev_alloc(c, &F->u_rhs, (size_t)L.nu)); XSB_CHK(dev_alloc(c, &F->u_sol, (size_t)L.nu));
   XSB_CHK(dev_alloc(c, &F->p_t1, (size_t)L.np)); XSB_CHK(dev_alloc(c, &F->p_t2, (size_t)L.np)); XSB_CHK(dev_alloc(c, &F->p_tmp, (size_t)L.np));
   return 0;

@@ -401,6 +401,7 @@ int ilu_setup(xsb_ctx c)
 {
   const Lattice &L = c->lat; cudaStream_t st = c->stream;
   if (c->slab.nranks > 1) XSB_CHK(build_owned_block(c, c->MpOwn)); else c->MpOwn = c->Mp;
+  if (c->slab.nranks == 1 && c->mp_block_a) c->MpOwn.a = c->mp_block_a;   // plain -fs tree emulating R ranks: cross-rank entries zeroed (xsb_fs.cu)
   const Csr &M = c->MpOwn;
   PLat P{L.PX, L.PY, c->slab.op1 - c->slab.op0};
   const int np = P.px * P.py * P.pz, nw = (P.px - 1) + 2 * (P.py - 1) + 4 * (P.pz - 1) + 1;

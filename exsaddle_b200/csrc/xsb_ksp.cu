@@ -164,7 +164,7 @@ static int read_solver_options(xsb_ctx c)
     o.has("fs_coarse");   // fieldsplit coarse solver: validated in mmg_setup / fsc_setup
   } else if (fs && o.str("saddle_fieldsplit_u_pc_type", "") != "mg") {
     s.pc_type = 4;   // plain -fs: PETSc's default sub-solvers (GMRES + ILU(0) on A00, nested Schur solves); validated in fsd_setup (xsb_fs.cu)
-    o.has("saddle_fieldsplit_u_ksp_type"); o.has("saddle_fieldsplit_p_ksp_type"); o.has("saddle_fieldsplit_u_ksp_max_it"); o.has("saddle_fieldsplit_p_pc_type");
+    o.has("saddle_fieldsplit_u_ksp_type"); o.has("saddle_fieldsplit_p_ksp_type"); o.has("saddle_fieldsplit_u_ksp_max_it"); o.has("saddle_fieldsplit_p_pc_type"); o.has("xsb_ranks");
   } else if (fs) {
     s.pc_type = 2;
     if (o.str("saddle_fieldsplit_u_ksp_type", "") != "gcr" || o.str("saddle_fieldsplit_p_ksp_type", "") != "preonly")
@@ -243,7 +243,7 @@ int ksp_release(xsb_ctx c)
   if (c->asmpc) { asm_free(c->asmpc); c->asmpc = nullptr; }
   dev_free_phase(c, 1);
   c->red = c->scal = nullptr; c->w_t1 = c->w_t2 = c->xdev = c->bdev = c->idiagA = c->gcr_r = c->fs_tu = nullptr;
-  c->mp_lu = c->mp_idiag = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
+  c->mp_lu = c->mp_idiag = nullptr; c->mp_block_a = nullptr; c->ilu_rows = c->ilu_lvl_off = c->ilu_diag = c->ilu_fcol = c->ilu_bcol = nullptr;
   c->ilu_fval = c->ilu_bval = c->ilu_binv = nullptr; c->ilu_fn = c->ilu_bn = nullptr; c->MpOwn = Csr();
   c->ilup_on = false; c->ilup_packf = c->ilup_packb = nullptr; c->ilup_prog = nullptr; c->ilup_y = nullptr;
   c->V.clear(); c->Z.clear(); c->GV.clear(); c->GS.clear();

@@ -1,6 +1,10 @@
-"""CPU oracle of the reference's plain `-fs` tree (exSaddle.c:303-322 with PETSc's default sub-solvers; goldens *_fs_1).
-TEST INFRASTRUCTURE, NOT PRODUCT.  Oracle only: the GPU library implements -fs with the abf.opts tree (GCR + GMG / preonly), not
-this one (ILU(0) of the assembled A00 in natural ordering is a ~5000-wavefront sequential sweep: not a GPU algorithm).
+"""CPU oracle of the reference's plain `-fs` tree (exSaddle.c:303-322 with PETSc's default sub-solvers; goldens *_fs_1, *_fs_2).
+TEST INFRASTRUCTURE, NOT PRODUCT (the product's version of this tree is exsaddle_b200/csrc/xsb_fs.cu).
+
+On more than one rank (goldens *_fs_2, `mpiexec -n 2`) PETSc's default PC of the two inner solves becomes bjacobi with one
+ILU(0) block per rank: the rank's rows / columns of A00 and of Mpscaled, i.e. the dofs its DMDAs own (velocity: default node
+split of the PETSC_DECIDE grid; pressure: the reference's rule, femixedspace.c:1216-1236 -- both restated in oracle_asm.py), in
+the rank-local ordering, which for the slab-shaped partitions of 2 ranks is the natural ordering restricted to the block.
 
   outer   GMRES(30), left PC, preconditioned norm, rtol 1e-5
   PC      PCFIELDSPLIT Schur / UPPER / user Mpscaled (App. B.2):
@@ -30,8 +34,43 @@ class Ilu0:
         return x
 
 
+class BlockIlu0:
+    """PCBJACOBI with ILU(0) blocks: z[block r] = ILU0(A[block r, block r])^-1 r[block r]"""
+
+    def __init__(self, A, blocks):
+        A = A.tocsr()
+        self.blocks = [(np.asarray(b), Ilu0(A[b][:, b])) for b in blocks]
+        cover = np.zeros(A.shape[0], int)
+        for b, _ in self.blocks:
+            cover[b] += 1
+        assert np.all(cover == 1), "bjacobi blocks must tile the rows"
+
+    def __call__(self, r):
+        z = np.empty_like(r)
+        for b, ilu in self.blocks:
+            z[b] = ilu(r[b])
+        return z
+
+
+def rank_blocks(nsd, mesh, nranks):
+    """(velocity dofs, pressure nodes) owned by each rank, ascending natural index (split-local numbering)"""
+    from .oracle_asm import subdomains
+    N = [2 * m + 1 for m in mesh[:nsd]]; P = [m + 1 for m in mesh[:nsd]]
+    _, sds = subdomains(nsd, mesh, nranks, 0)
+    ub, pb = [], []
+    for sd in sds:
+        u = [np.arange(*sd["own_u"][d]) for d in range(nsd)]; p = [np.arange(*sd["own_p"][d]) for d in range(nsd)]
+        if nsd == 2:
+            un = (u[1][:, None] * N[0] + u[0][None, :]).ravel(); pn = (p[1][:, None] * P[0] + p[0][None, :]).ravel()
+        else:
+            un = ((u[2][:, None, None] * N[1] + u[1][None, :, None]) * N[0] + u[0][None, None, :]).ravel()
+            pn = ((p[2][:, None, None] * P[1] + p[1][None, :, None]) * P[0] + p[0][None, None, :]).ravel()
+        ub.append(np.sort((un[:, None] * nsd + np.arange(nsd)[None, :]).ravel())); pb.append(np.sort(pn))
+    return ub, pb
+
+
 class FieldSplitDefault:
-    def __init__(self, opts, nsd=3, lame=False):
+    def __init__(self, opts, nsd=3, lame=False, nranks=1):
         self.o = O.parse_options(opts) if not isinstance(opts, dict) else dict(opts)
         o = self.o
         if "fs" not in o or "mg" in o:
@@ -40,7 +79,12 @@ class FieldSplitDefault:
         p = self.p; nu = p.nu; self.nu = nu
         A = p.A().scipy().tocsr(); self.A = A
         self.A00 = A[:nu, :nu].tocsr(); self.A01 = A[:nu, nu:].tocsr(); self.A10 = A[nu:, :nu].tocsr(); self.A11 = A[nu:, nu:].tocsr()
-        self.ilu_u = Ilu0(self.A00); self.ilu_p = Ilu0(p.Mp().scipy())
+        if nranks == 1:
+            self.ilu_u = Ilu0(self.A00); self.ilu_p = Ilu0(p.Mp().scipy())
+        else:   # bjacobi + ILU(0) per rank on both splits
+            mx = int(o.get("mx", 4)); mesh = (mx, int(o.get("my", mx)), int(o.get("mz", mx)) if nsd == 3 else 1)
+            ub, pb = rank_blocks(nsd, mesh, nranks)
+            self.ilu_u = BlockIlu0(self.A00, ub); self.ilu_p = BlockIlu0(p.Mp().scipy(), pb)
         self.u_max_it = int(o.get("saddle_fieldsplit_u_ksp_max_it", 10000))
         self.p_preonly = o.get("saddle_fieldsplit_p_ksp_type", "gmres") == "preonly"
         self.u_its = []

@@ -403,12 +403,14 @@ def test_golden_monolithic_mg_output_is_identical(kat, name):
 
 
 # ------------------------------------------------------------------ plain -fs tree: PETSc's default sub-solvers (xsb_fs.cu)
-@pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1"])
+@pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1",
+                                  "exSaddle3d_fs_2", "exSaddle2d_fs_2", "exSaddle2d_lame_fs_2", "exSaddle3d_lame_fs_2"])
 def test_golden_plain_fs_output_is_identical(kat, name):
     """`-fs` without abf.opts (exSaddle.c:303-322, Makefile:282, 347, 396, 480): GMRES + fieldsplit Schur-upper with GMRES + ILU(0)
     of A00 and of Mpscaled, a nested velocity solve inside every Schur-complement product.  The program output (banner, residual
-    history as printed by -saddle_ksp_monitor_short, converged-reason line where asked, diagnostics) diffs clean against testref."""
-    c, text, s, x = _run(kat, name)
+    history as printed by -saddle_ksp_monitor_short, converged-reason line where asked, diagnostics) diffs clean against testref.
+    *_fs_2: the reference on 2 ranks (-xsb_ranks 2): both ILU(0)s become bjacobi with one block per rank."""
+    c, text, s, x = _run(kat, name, nranks=kat[name]["nranks"])
     ref = list(c["banner"]) + ["  Residual norms for saddle_ solve."] + ["%3d KSP Residual norm %s" % (i, t) for i, t in enumerate(c["residuals_text"])]
     got = [l.rstrip() for l in text.rstrip("\n").split("\n")]
     if "-saddle_ksp_converged_reason" in c["options"]:

@@ -533,13 +533,16 @@ def test_asm_subdomains_host_logic_matches_oracle_and_tiles_the_mesh():
 
 
 # ---- the reference's plain -fs tree with PETSc's default sub-solvers (oracle only; oracle/oracle_fs.py) ----
-@pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1"])
+@pytest.mark.parametrize("name", ["exSaddle3d_fs_1", "exSaddle2d_fs_1", "exSaddle2d_lame_fs_1", "exSaddle3d_lame_fs_1",
+                                  "exSaddle3d_fs_2", "exSaddle2d_fs_2", "exSaddle2d_lame_fs_2", "exSaddle3d_lame_fs_2"])
 def test_plain_fs_tree_history_and_diagnostics_match_golden(kat, name):
     """GMRES + PCFIELDSPLIT Schur / UPPER / user Mpscaled with GMRES + ILU(0) on both splits and the nested A00 solve inside every
-    Schur-complement product (App. B.2): residual history and diagnostics to every printed digit of testref/*_fs_1.ref."""
+    Schur-complement product (App. B.2): residual history and diagnostics to every printed digit of testref/*_fs_1.ref; and of
+    testref/*_fs_2.ref, the reference on 2 ranks, where the inner PCs are bjacobi with one ILU(0) block per rank on the dofs the
+    rank's DMDAs own (the same ownership restatement the ASM goldens pin)."""
     from oracle.oracle_fs import FieldSplitDefault
     c = kat[name]
-    F = FieldSplitDefault(c["options"], nsd=c["nsd"], lame=c["lame"])
+    F = FieldSplitDefault(c["options"], nsd=c["nsd"], lame=c["lame"], nranks=c["nranks"])
     x, its, reason, hist = F.solve()
     assert reason == 2 and its == len(c["residuals"]) - 1
     assert [_short(v) for v in hist] == c["residuals_text"]
