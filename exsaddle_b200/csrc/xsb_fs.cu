@@ -125,9 +125,10 @@ int gilu_setup(xsb_ctx c, const Csr &M, GIlu &I)
   I.nlf = nlf; I.nlb = nlb;
   XSB_CHK(dev_alloc(c, &I.diag, (size_t)n)); XSB_CHK(dev_alloc(c, &I.lu, (size_t)M.nnz));
   XSB_CHK(dev_alloc(c, &I.foff, (size_t)nlf + 1)); XSB_CHK(dev_alloc(c, &I.frows, (size_t)n)); XSB_CHK(dev_alloc(c, &I.boff, (size_t)nlb + 1)); XSB_CHK(dev_alloc(c, &I.brows, (size_t)n));
-  CUDA_OK(cudaMemcpy(I.diag, diag.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(I.foff, foff.data(), sizeof(int) * (nlf + 1), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(I.frows, frows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(I.boff, boff.data(), sizeof(int) * (nlb + 1), cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(I.brows, brows.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  // uploads on the handle's stream (ordered with the kernels that read them; the host vectors outlive the synchronisation below)
+  CUDA_OK(cudaMemcpyAsync(I.diag, diag.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(I.foff, foff.data(), sizeof(int) * (nlf + 1), cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(I.frows, frows.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(I.boff, boff.data(), sizeof(int) * (nlb + 1), cudaMemcpyHostToDevice, st)); CUDA_OK(cudaMemcpyAsync(I.brows, brows.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(I.lu, M.a, sizeof(double) * M.nnz, cudaMemcpyDeviceToDevice, st));
   int *flag = nullptr; XSB_CHK(dev_alloc(c, &flag, 1));
   k_gilu_factor<<<1, 1024, 0, st>>>(nlf, I.foff, I.frows, I.ia, I.ja, I.diag, I.lu, flag); KERNEL_OK();
