@@ -466,6 +466,20 @@ def test_monolithic_mg_option_errors_like_reference():
         g.close()
 
 
+def test_asm_and_fs_coarse_option_errors_like_reference():
+    """exSaddle.c:210, 212 and the limits of the ASM / -fs_coarse support, each with its message."""
+    for opts, frag in (("-mx 4 -fs_coarse -saddle_pc_type jacobi", "-fs_coarse supplied without -mg"),
+                       ("-mx 4 -fs -set_ksp_dm", "-set_ksp_dm not intended for use with -mg or -fs"),
+                       ("-mx 4 -saddle_pc_type asm", "-saddle_pc_asm_dm_subdomains -set_ksp_dm"),
+                       ("-mx 4 -saddle_pc_type asm -saddle_pc_asm_dm_subdomains -set_ksp_dm", "ASM sub-solves"),
+                       ("-mx 2 -saddle_pc_type asm -saddle_pc_asm_dm_subdomains -set_ksp_dm -saddle_sub_pc_type lu -xsb_ranks 9", "Cannot generate consistent macro element")):
+        g = X.ExSaddle(opts, nsd=3).assemble()
+        with pytest.raises(X.XsbError) as e:
+            g.ksp_setup()
+        assert frag in str(e.value), (opts, str(e.value))
+        g.close()
+
+
 def test_golden_monolithic_mg_fs_coarse(kat):
     """-mg -fs_coarse (exSaddle.c:362-400, Makefile:390): the coarse saddle level solved by FGMRES preconditioned with fieldsplit
     Schur / UPPER / user Mpscaled_coarse (GMRES + Jacobi splits, nested velocity solve inside the Schur complement), on the device.
