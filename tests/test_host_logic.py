@@ -253,3 +253,56 @@ def test_gradient_block_from_the_products_1d_tables_equals_the_oracles_assembled
     bi, _ = p.bc(); keep = np.ones(nu, bool); keep[bi[bi < nu]] = False
     D = (sp.diags(keep.astype(float)) @ B - A01).tocoo()
     assert np.max(np.abs(D.data), initial=0.0) <= 1e-14 * np.max(np.abs(A01.data))
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_gradient_tables_on_a_slab_lattice_give_the_global_rows_of_the_owned_planes(nranks):
+    """Slabs apply the gradient / divergence stencils on the rank's LOCAL lattice (element layers [k0-2, k1+1)), whose ends are treated
+    like mesh boundaries.  Claim: for the planes a rank OWNS this gives the rows of the global blocks -- every element around an owned
+    node lies inside the local lattice.  Checked with the product's tables (z direction: local element count) against the oracle's
+    global A[u,p] and A[p,u], rank by rank."""
+    import scipy.sparse as sp
+    from oracle import oracle as O
+    mx, my, mz = 3, 2, 6
+    p = O.Problem("-model 6 -mx %d -my %d -mz %d -eta1 10" % (mx, my, mz), nsd=3)
+    nu = p.nu; A = p.A().scipy().tocsr(); A01 = A[:nu, nu:].toarray(); A10 = A[nu:, :nu].toarray()
+    NX, NY, PX, PY = 2 * mx + 1, 2 * my + 1, mx + 1, my + 1
+    bi, _ = p.bc(); free = np.ones(nu, bool); free[bi[bi < nu]] = False
+
+    def dense(m, h):
+        uP, uM, uG, _, _ = X.grad_line_tables(m, h)
+        M = np.zeros((2 * m + 1, m + 1)); G = np.zeros_like(M)
+        for i in range(2 * m + 1):
+            for a in range(3):
+                if uP[i, a] >= 0:
+                    M[i, uP[i, a]] += uM[i, a]; G[i, uP[i, a]] += uG[i, a]
+        return M, G
+    Mx, Gx = dense(mx, 0.5 / mx); My, Gy = dense(my, 0.5 / my)
+    for r in range(nranks):
+        lay = X.slab_layout(3, mx, my, mz, nranks, r)
+        e0, e1, k0, k1 = lay["e0"], lay["e1"], lay["k0"], lay["k1"]
+        last = r == nranks - 1
+        Mz, Gz = dense(e1 - e0, 0.5 / mz)                                   # the local lattice in z
+        for kl in range(2 * (k0 - e0), 2 * (k1 - e0) + (1 if last else 0)):  # owned velocity planes (local index)
+            kg = kl + 2 * e0
+            for j in range(NY):
+                for i in range(NX):
+                    node = i + NX * (j + NY * kg)
+                    for c in range(3):
+                        fx, fy, fz = (Gx if c == 0 else Mx)[i], (Gy if c == 1 else My)[j], (Gz if c == 2 else Mz)[kl]
+                        row = np.zeros((mz + 1, PY, PX))
+                        row[e0:e1 + 1] = -np.einsum("k,j,i->kji", fz, fy, fx)
+                        want = A01[3 * node + c].reshape(mz + 1, PY, PX)
+                        got = row if free[3 * node + c] else np.zeros_like(row)
+                        assert np.max(np.abs(got - want)) <= 1e-14, (r, kl, j, i, c)
+        for Pl in range(k0 - e0, k1 - e0 + (1 if last else 0)):            # owned pressure planes: rows of A10 = columns of the same stencil
+            Pg = Pl + e0
+            for Pj in range(PY):
+                for Pi in range(PX):
+                    want = A10[Pi + PX * (Pj + PY * Pg)].reshape(2 * mz + 1, NY, NX, 3)
+                    got = np.zeros_like(want)
+                    for c in range(3):
+                        fx, fy, fz = (Gx if c == 0 else Mx)[:, Pi], (Gy if c == 1 else My)[:, Pj], (Gz if c == 2 else Mz)[:, Pl]
+                        got[2 * e0:2 * e1 + 1, :, :, c] = -np.einsum("k,j,i->kji", fz, fy, fx)
+                    got = got * free.reshape(2 * mz + 1, NY, NX, 3)
+                    assert np.max(np.abs(got - want)) <= 1e-14, (r, Pl, Pj, Pi)
